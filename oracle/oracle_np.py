@@ -1,0 +1,278 @@
+"""CPU oracle for the STFT + varispeed-resample hot path (numpy restatement).
+
+TEST INFRASTRUCTURE ONLY.  Nothing in ``pyaudiorestoration_b200`` may import this
+module; only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
+``--impl reference`` legs use it, and there only as the checker / the reported baseline.
+
+Every function restates one function of the reference (HENDRIX-ZT2/pyaudiorestoration,
+paths relative to the reference root) and cites the lines it follows.  The reference
+holds no golden vectors or tests for this path, so the oracle is
+pinned by fixtures generated from the reference itself, imported and run unmodified in
+the authoring container: ``tests/golden/make_golden.py`` -> ``tests/golden/*.npz``
+(checked by ``tests/test_oracle_golden.py``).
+
+Third-party arithmetic the reference delegates to (not vendored in the reference):
+numpy pocketfft (``np.fft.rfft/irfft``, numpy 2.3.5 in this image, unpinned in the
+reference's requirements.txt), ``scipy.signal.get_window`` (scipy 1.18.1 here) and
+``np.sinc`` / ``np.hanning``.  The oracle calls the same numpy/scipy entry points.
+"""
+import numpy as np
+from scipy import signal as dsp
+
+__all__ = [
+    "get_window_f32", "reflect_pad", "stft_ref", "stft_f64", "to_mag", "istft_ref",
+    "window_sumsquare", "fix_length", "speed_to_pos", "speed_segments",
+    "sinc_resample", "hanning_f32", "linear_resample", "lag_to_positions",
+]
+
+
+# --------------------------------------------------------------------------- STFT
+
+def get_window_f32(window_name, n_fft):
+    """Periodic scipy window cast to float32 -- util/fourier.py:66."""
+    return dsp.get_window(window_name, int(n_fft)).astype(np.float32)
+
+
+def reflect_pad(x, n_fft):
+    """util/fourier.py:78-82 (estimate_and_center): np.pad(x, n_fft//2, 'reflect')."""
+    return np.pad(x, int(n_fft // 2), mode="reflect")
+
+
+def n_frames(length, n_fft, step):
+    """Frame count of the centred transform -- util/fourier.py:81."""
+    return (length + 2 * (n_fft // 2) - n_fft) // step + 1
+
+
+def stft_ref(x, n_fft=1024, step=512, window_name="blackmanharris", zeropad=1):
+    """The reference's numpy back-end, same operations in the same precision.
+
+    util/fourier.py:37-75 (stft: int coercion, 1-D check, float32 periodic window) and
+    :136-157 (np_rfft_pick: reflect pad, per-frame ``np.fft.rfft(window * frame, n=N*Z)``
+    for n_fft > 512, the vectorised segment_array path :160-166 otherwise, then
+    ``/ sqrt(n_fft)``).  Result is (N*Z/2+1, T), complex128 after the division (numpy 2.x).
+    """
+    n_fft = int(n_fft)
+    step = max(n_fft // 2, 1) if step is None else int(step)
+    x = np.asarray(x)
+    if x.ndim != 1:
+        raise ValueError("x must be 1D")
+    window = get_window_f32(window_name, n_fft)
+    xp = reflect_pad(x, n_fft)
+    t = (len(xp) - n_fft) // step + 1
+    nz = n_fft * zeropad
+    if n_fft > 512:
+        cdt = np.complex64 if xp.dtype == np.float32 else (
+            np.complex128 if xp.dtype == np.float64 else np.complex64)
+        out = np.empty((nz // 2 + 1, t), dtype=cdt, order="F")
+        for i in range(t):
+            out[:, i] = np.fft.rfft(window * xp[i * step: i * step + n_fft], n=nz)
+    else:
+        fft_in = np.zeros((nz, t), dtype=np.float32)
+        for i in range(t):
+            fft_in[:n_fft, i] = window * xp[i * step: i * step + n_fft]
+        out = np.fft.rfft(fft_in, axis=0)
+    return out / np.sqrt(n_fft)
+
+
+def stft_f64(x, n_fft=1024, step=512, window_name="blackmanharris", zeropad=1):
+    """fp64 "truth" of the same transform (SURVEY.md 8c restatement rules): float32-rounded
+    window and float32 input, all arithmetic in float64, left-aligned frame with zeros
+    appended (util/fourier.py:164-166), scale 1/sqrt(n_fft) (:157).  Returns C-order
+    (T, F) complex128 -- i.e. the memory image of the reference's F-ordered (F, T)."""
+    n_fft = int(n_fft)
+    step = max(n_fft // 2, 1) if step is None else int(step)
+    x = np.asarray(x)
+    if x.ndim != 1:
+        raise ValueError("x must be 1D")
+    window = get_window_f32(window_name, n_fft).astype(np.float64)
+    xp = reflect_pad(np.asarray(x, dtype=np.float32), n_fft).astype(np.float64)
+    t = (len(xp) - n_fft) // step + 1
+    nz = n_fft * zeropad
+    idx = np.arange(n_fft)[None, :] + step * np.arange(t)[:, None]
+    out = np.empty((t, nz // 2 + 1), dtype=np.complex128)
+    blk = max(1, (1 << 24) // nz)
+    for s in range(0, t, blk):
+        e = min(t, s + blk)
+        out[s:e] = np.fft.rfft(xp[idx[s:e]] * window[None, :], n=nz, axis=1)
+    out /= np.sqrt(n_fft)
+    return out
+
+
+def to_mag(spectrum):
+    """util/fourier.py:23-24."""
+    return abs(spectrum) + .0000001
+
+
+# --------------------------------------------------------------------------- iSTFT
+
+def fix_length(data, size, axis=-1, **kwargs):
+    """util/fourier.py:440-478."""
+    kwargs.setdefault("mode", "constant")
+    n = data.shape[axis]
+    if n > size:
+        sl = [slice(None)] * data.ndim
+        sl[axis] = slice(0, size)
+        return data[tuple(sl)]
+    if n < size:
+        lengths = [(0, 0)] * data.ndim
+        lengths[axis] = (0, size - n)
+        return np.pad(data, lengths, **kwargs)
+    return data
+
+
+def window_sumsquare(window_name, n_frames_, hop_length, n_fft, dtype=np.float32):
+    """util/fourier.py:492-546 with win_length == n_fft, norm=None; fill loop :481-489."""
+    n = n_fft + hop_length * (n_frames_ - 1)
+    x = np.zeros(n, dtype=dtype)
+    win_sq = dsp.get_window(window_name, n_fft) ** 2
+    for i in range(n_frames_):
+        s = i * hop_length
+        x[s:min(n, s + n_fft)] += win_sq[:max(0, min(n_fft, n - s))]
+    return x
+
+
+def istft_ref(stft_matrix, hop_length=None, window_name="blackmanharris", length=None,
+              dtype=None):
+    """util/fourier.py:314-437 with win_length=None, center=True.  Does NOT reproduce the
+    in-place ``stft_matrix *= sqrt(n_fft)`` side effect (:359) -- works on a copy.
+    Accumulates in the output dtype exactly like the reference (:383-404)."""
+    stft_matrix = np.array(stft_matrix)
+    n_fft = 2 * (stft_matrix.shape[0] - 1)
+    stft_matrix = stft_matrix * np.asarray(np.sqrt(n_fft), dtype=stft_matrix.real.dtype)
+    if hop_length is None:
+        hop_length = int(n_fft // 4)
+    window = dsp.get_window(window_name, n_fft, fftbins=True)[:, None]
+    if length:
+        padded = length + int(n_fft)
+        nfr = min(stft_matrix.shape[1], int(np.ceil(padded / hop_length)))
+    else:
+        nfr = stft_matrix.shape[1]
+    if dtype is None:
+        dtype = np.float32 if stft_matrix.dtype == np.complex64 else np.float64
+    y = np.zeros(n_fft + hop_length * (nfr - 1), dtype=dtype)
+    ncol = max((2 ** 18) // (stft_matrix.shape[0] * stft_matrix.itemsize), 1)
+    frame = 0
+    for s in range(0, nfr, ncol):
+        e = min(s + ncol, nfr)
+        ytmp = window * np.fft.irfft(stft_matrix[:, s:e], axis=0)
+        for f in range(e - s):
+            a = (frame + f) * hop_length
+            y[a:a + n_fft] += ytmp[:, f]
+        frame += e - s
+    wss = window_sumsquare(window_name, nfr, hop_length, n_fft, dtype=dtype)
+    nz = wss > np.finfo(wss.dtype).tiny
+    y[nz] /= wss[nz]
+    if length is None:
+        return y[n_fft // 2:-(n_fft // 2)]
+    return fix_length(y[n_fft // 2:], length)
+
+
+# --------------------------------------------------------------------------- positions
+
+def speed_segments(sampletimes, speeds):
+    """Integer segment lengths of util/resampling.py:111-118: error-diffused
+    ``n = int(round(period * mean(speeds[i:i+2]) + err))`` (Python round = half-even)."""
+    sampletimes = np.asarray(sampletimes, dtype=np.float64)
+    speeds = np.asarray(speeds, dtype=np.float64)
+    periods = np.diff(sampletimes)
+    err = 0.0
+    ns = np.empty(len(speeds) - 1, dtype=np.int64)
+    for i in range(len(speeds) - 1):
+        inerr = periods[i] * ((speeds[i] + speeds[i + 1]) / 2.0) + err
+        n = int(round(inerr))
+        err = inerr - n
+        ns[i] = n
+    return ns
+
+
+def speed_to_pos(sampletimes, speeds, num_input_samples):
+    """util/resampling.py:93-137.  Returns only the filled prefix: where the reference's end
+    test (:129) never fires it returns its np.empty buffer with an uninitialised tail;
+    parity is defined on ``pos[0:sum(n)]``."""
+    sampletimes = np.asarray(sampletimes, dtype=np.float64)
+    speeds = np.asarray(speeds, dtype=np.float64)
+    ns = speed_segments(sampletimes, speeds)
+    offset = sampletimes[0]
+    out = np.empty(int(ns.sum()), dtype=np.float64)
+    o = 0
+    for i, n in enumerate(ns):
+        n = int(n)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            block_speeds = np.arange(n) / (n - 1) * (speeds[i + 1] - speeds[i]) + speeds[i]
+            sample_at = np.cumsum(1 / block_speeds) + offset
+        offset = sample_at[-1]
+        out[o:o + n] = sample_at
+        if out[o] <= num_input_samples <= out[o + n - 1]:
+            end = o + int(np.argmin(np.abs(sample_at - num_input_samples)))
+            return out[:end]
+        o += n
+    return out[:o]
+
+
+def lag_to_positions(lag_curve, sr, n_in):
+    """Positions for the lag-curve mode of run -- util/resampling.py:189-206."""
+    sampletimes = lag_curve[:, 0] * sr
+    lags = lag_curve[:, 1] * sr
+    num_out = n_in + abs(lags[-1])
+    sample_at = np.interp(np.arange(num_out), sampletimes, sampletimes - lags)
+    hit = np.nonzero(sample_at >= n_in)[0]
+    if len(hit):
+        sample_at = sample_at[:hit[0]]
+    np.clip(sample_at, 0, None, out=sample_at)
+    return sample_at
+
+
+# --------------------------------------------------------------------------- resampler
+
+def hanning_f32(nt):
+    """util/resampling.py:24,36."""
+    return np.hanning(2 * nt + 1).astype(np.float32)
+
+
+def sinc_resample(sample_at, signal, nt, block=4096):
+    """util/resampling.py:51-90 (sinc_core) as a single thread sees it, vectorised over
+    output samples, all arithmetic in float64, store float32.
+
+    Reproduced quirks: half-even rounding of the position (:69), taps
+    ``lower = max(0, ind-NT) .. upper = min(ind+NT, len_in)`` -- the +NT tap dropped
+    (:71-72); weights/window always indexed from 0 even when ``lower`` was clamped
+    (start-edge misalignment, :89-90); ``period_to`` of the last element reuses the
+    previous one (:76-77); ``fc = min(1/period_to, 1)`` (:79); empty slice -> 0.
+    """
+    sample_at = np.asarray(sample_at, dtype=np.float64)
+    signal = np.asarray(signal)
+    m = len(sample_at)
+    len_in = len(signal)
+    out = np.zeros(m, dtype=np.float32)
+    if m == 0:
+        return out
+    win = hanning_f32(nt).astype(np.float64)[: 2 * nt]
+    n_arr = np.arange(-nt, nt + 1, dtype=np.float32).astype(np.float64)[: 2 * nt]
+    period = np.empty(m, dtype=np.float64)
+    period[:-1] = np.maximum(0.000000000001, sample_at[1:] - sample_at[:-1])
+    period[-1] = period[-2] if m > 1 else 0.0
+    sig64 = signal.astype(np.float64)
+    k = np.arange(2 * nt)
+    for s in range(0, m, block):
+        e = min(m, s + block)
+        p = sample_at[s:e]
+        ind = np.rint(p).astype(np.int64)
+        lower = np.maximum(0, ind - nt)
+        upper = np.minimum(ind + nt, len_in)
+        cnt = np.maximum(upper - lower, 0)
+        with np.errstate(divide="ignore"):
+            fc = np.minimum(1.0 / period[s:e], 1.0)
+        shift = p - ind
+        si = np.sinc((n_arr[None, :] - shift[:, None]) * fc[:, None]) * fc[:, None]
+        idx = lower[:, None] + k[None, :]
+        valid = k[None, :] < cnt[:, None]
+        sig = np.where(valid, sig64[np.clip(idx, 0, max(len_in - 1, 0))], 0.0) if len_in else \
+            np.zeros(idx.shape)
+        out[s:e] = np.sum(sig * si * win[None, :], axis=1).astype(np.float32)
+    return out
+
+
+def linear_resample(sample_at, signal):
+    """The "Linear" mode of run -- util/resampling.py:228-229."""
+    return np.interp(sample_at, np.arange(len(signal)), signal, left=0.0, right=0.0).astype(
+        np.float32)
