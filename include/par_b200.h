@@ -1,0 +1,137 @@
+/*
+ * par_b200.h -- C ABI of libpar_b200.so: the B200-native STFT + varispeed-resample hot path
+ * of HENDRIX-ZT2/pyaudiorestoration (util/fourier.py, util/resampling.py).
+ *
+ * The reference is pure Python and has NO FFI of its own: its boundary is the
+ * module surface util.fourier.* / util.resampling.run.  Every entry point below names the
+ * reference function (file:line, relative to the reference root) whose work it replaces; the
+ * Python mirror of that surface (pyaudiorestoration_b200/util/{fourier,resampling}.py) is a thin
+ * ctypes caller of this header.  INTEGRATION.md shows the two-line stubs a maintainer drops into
+ * the reference's util/ package.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no C++/torch types.
+ *  - Every function returns 0 (PAR_OK) or a negative PAR_E* code; the message of the last error
+ *    on the calling thread is par_last_error().  No exceptions cross the boundary.
+ *  - The caller owns all data buffers.  Without PAR_DEVICE_PTRS the data pointers are HOST
+ *    memory (pinned or pageable): the call stages through device memory, runs, copies back and
+ *    returns when the result is in the host buffer.  With PAR_DEVICE_PTRS they are device
+ *    pointers on `device`, work is enqueued on `stream` (a cudaStream_t, NULL = default stream)
+ *    and the call returns without synchronising.
+ *  - Small parameter arrays (window, speed curve) are always HOST pointers.
+ *  - Every entry sets the CUDA device itself and is re-entrant (the reference calls this path
+ *    from QThread workers, util/qt_threads.py:19-35); caches are mutex-guarded.
+ *  - There is no CPU fallback: without a usable CUDA device every compute entry fails with
+ *    PAR_ECUDA.
+ *
+ * Layouts
+ *  - Audio is float32.  A channel is `n` samples `stride` elements apart; channel c starts
+ *    `c * ch_stride` elements after the base pointer (planar: stride 1, ch_stride >= n;
+ *    the reference's interleaved (frames, channels) arrays: stride C, ch_stride 1).
+ *  - A spectrogram is the memory image of the reference's F-ordered (F, T) array: frame t of
+ *    channel c starts at  c * out_ch_stride + t * out_pitch  elements (complex64 = 2 floats, or
+ *    float32 magnitudes), bins contiguous; F = n_fft*zeropad/2 + 1, out_pitch >= F.
+ */
+#ifndef PAR_B200_H
+#define PAR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PAR_API __attribute__((visibility("default")))
+#else
+#define PAR_API
+#endif
+
+#define PAR_OK 0
+#define PAR_EINVAL (-1)      /* bad argument */
+#define PAR_ECUDA (-2)       /* CUDA runtime error / no device */
+#define PAR_EUNSUPPORTED (-3)/* valid request this build cannot run (e.g. n_fft not a power of two) */
+#define PAR_ECAPACITY (-4)   /* output buffer too small; required size returned where documented */
+
+/* flags */
+#define PAR_DEVICE_PTRS (1u << 0)   /* data pointers are device memory; async on `stream` */
+#define PAR_OUT_MAGNITUDE (1u << 1) /* par_stft_f32: write float32 |S| + 1e-7 instead of complex64 */
+#define PAR_SINC_ALIGNED_EDGES (1u << 2) /* par_sinc_resample_f32: do NOT reproduce the reference's
+                                            start-edge tap misalignment */
+
+/* ---- diagnostics ------------------------------------------------------------------------- */
+PAR_API const char *par_last_error(void);
+PAR_API const char *par_version(void);
+PAR_API int par_device_count(void);
+/* number of kernels this library has launched since load (for bench.py's gpu_launches) */
+PAR_API int64_t par_kernel_launch_count(void);
+/* CUDA-event time of the last compute kernel sequence of a HOST-pointer call, in ms, on the
+ * calling thread (0 if none); informational. */
+PAR_API double par_last_kernel_ms(void);
+
+/* Pinned host allocations (the Python layer returns ndarrays backed by these so that the
+ * device->host copy of a result runs at full PCIe rate). */
+PAR_API void *par_host_alloc(int64_t bytes);
+PAR_API void par_host_free(void *p);
+
+/* ---- STFT: util/fourier.py:37-75 stft, :78-82 estimate_and_center, :160-166 segment_array,
+ *      :124-157 pyfftw_rfft2 / np_rfft_pick, :92-121 torch_rfft2, :23-29 to_mag / get_mag ------
+ * Number of frames of the centred transform (util/fourier.py:81): n // hop + 1 for even n_fft. */
+PAR_API int64_t par_stft_num_frames(int64_t n, int n_fft, int hop);
+
+/* Fused reflect-pad + frame gather + window + real FFT of length n_fft*zeropad (frame
+ * left-aligned, zeros appended) + 1/sqrt(n_fft) scaling, for n_ch channels in one launch.
+ * window: HOST float32[n_fft].  out: complex64 (or float32 with PAR_OUT_MAGNITUDE).
+ * n_fft*zeropad must be a power of two in [32, 32768]; n >= 1. */
+PAR_API int par_stft_f32(const float *x, int64_t n, int64_t x_stride, int n_ch, int64_t x_ch_stride,
+                 int n_fft, int hop, int zeropad, const float *window,
+                 void *out, int64_t out_pitch, int64_t out_ch_stride,
+                 unsigned flags, int device, void *stream);
+
+/* ---- iSTFT: util/fourier.py:314-437 istft (+ :677-687 __overlap_add, :481-546 window_sumsquare)
+ * S: complex64 frames (layout above, F = n_fft/2+1 bins, n_frames frames per channel), already
+ * trimmed to the frames the reference would use (:373-381).  Computes
+ *   y[j] = sum_t w[j-t*hop] * irfft(S[:,t] * sqrt(n_fft))[j-t*hop] / sum_t w[j-t*hop]^2
+ * over the padded timeline, skips `start` samples (n_fft/2 when centred) and writes `length`
+ * samples (zero-filled past the end of the timeline).  window: HOST float32[n_fft]. */
+PAR_API int par_istft_f32(const void *S, int n_fft, int64_t n_frames, int64_t s_pitch, int n_ch,
+                  int64_t s_ch_stride, int hop, const float *window, int64_t start,
+                  int64_t length, float *y, int64_t y_stride, int64_t y_ch_stride,
+                  unsigned flags, int device, void *stream);
+
+/* ---- positions: util/resampling.py:93-137 speed_to_pos --------------------------------------
+ * Host-only, serial, bit-exact: the error-diffused integer segment lengths (:111-118).
+ * seg_n: int64[k-1].  Returns sum(seg_n) in *total. */
+PAR_API int par_speed_segments(const double *sampletimes, const double *speeds, int64_t k,
+                       int64_t *seg_n, int64_t *total);
+
+/* Expands the speed curve into float64 read positions with the reference's operation order
+ * (per-segment sequential cumsum of 1/speed, carried offset, end test + argmin trim).
+ * sampletimes/speeds: HOST float64[k].  pos: capacity `cap` doubles (host, or device with
+ * PAR_DEVICE_PTRS); cap >= sum(seg_n) always suffices.  *m receives the number of valid
+ * positions (the reference's filled prefix).  The expansion runs on the GPU;
+ * the call synchronises `stream` internally (it needs the per-segment sums on the host). */
+PAR_API int par_speed_to_pos_f64(const double *sampletimes, const double *speeds, int64_t k,
+                         double num_input_samples, double *pos, int64_t cap, int64_t *m,
+                         unsigned flags, int device, void *stream);
+
+/* ---- resampler: util/resampling.py:51-90 sinc_core, :21-46 sinc_wrapper(_mt) ----------------
+ * out[i] = sum_k signal[lower+k] * fc*sinc((k-NT-shift)*fc) * hanning(2NT+1)[k] with the
+ * reference's index rules (half-even rounding, +NT tap dropped, fc = min(1/period, 1), the last
+ * element reuses the previous period; start-edge misalignment unless PAR_SINC_ALIGNED_EDGES).
+ * pos: float64[m], shared by all channels.  1 <= nt <= 512. */
+PAR_API int par_sinc_resample_f32(const double *pos, int64_t m, const float *signal, int64_t n_in,
+                          int64_t sig_stride, int n_ch, int64_t sig_ch_stride, int nt,
+                          float *out, int64_t out_stride, int64_t out_ch_stride,
+                          unsigned flags, int device, void *stream);
+
+/* "Linear" mode of run: util/resampling.py:228-229 (np.interp, left = right = 0). */
+PAR_API int par_linear_resample_f32(const double *pos, int64_t m, const float *signal, int64_t n_in,
+                            int64_t sig_stride, int n_ch, int64_t sig_ch_stride,
+                            float *out, int64_t out_stride, int64_t out_ch_stride,
+                            unsigned flags, int device, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAR_B200_H */

@@ -1,0 +1,531 @@
+// api.cu -- the C ABI of libpar_b200.so (include/par_b200.h): argument checking, host<->device
+// staging for HOST-pointer calls, cached constant tables, and the serial host part of
+// speed_to_pos.  No CPU implementation of any kernel lives here: without a CUDA device every
+// compute entry fails with PAR_ECUDA.
+#include <math.h>
+#include <string.h>
+
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/par_b200.h"
+#include "fft_core.cuh"
+#include "par_internal.h"
+
+namespace par {
+
+static thread_local std::string g_err;
+static thread_local double g_last_ms = 0.0;
+static std::atomic<int64_t> g_launches{0};
+static std::mutex g_mu;
+
+void set_error(const std::string &msg) { g_err = msg; }
+int cuda_fail(cudaError_t e, const char *what) {
+	g_err = std::string(what) + ": " + cudaGetErrorString(e);
+	cudaGetLastError();   // clear sticky-less errors
+	return PAR_ECUDA;
+}
+void count_launch(int n) { g_launches += n; }
+
+int sm_count(int device) {
+	static int cache[64] = {0};
+	if (device >= 0 && device < 64 && cache[device]) return cache[device];
+	int n = 0;
+	if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || n <= 0) n = 148;
+	if (device >= 0 && device < 64) cache[device] = n;
+	return n;
+}
+
+// ---- cached device tables ---------------------------------------------------------------------
+struct TableKey {
+	int device, kind, a;
+	uint64_t hash;
+	bool operator<(const TableKey &o) const {
+		if (device != o.device) return device < o.device;
+		if (kind != o.kind) return kind < o.kind;
+		if (a != o.a) return a < o.a;
+		return hash < o.hash;
+	}
+};
+static std::map<TableKey, void *> g_tables;
+
+static void *upload_table(const TableKey &key, const void *host, size_t bytes, cudaStream_t st) {
+	// caller holds g_mu
+	void *d = nullptr;
+	if (cudaMalloc(&d, bytes) != cudaSuccess) { cuda_fail(cudaGetLastError(), "cudaMalloc(table)"); return nullptr; }
+	// synchronous copy from pageable memory: the table is complete before any kernel can use it
+	if (cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+		cuda_fail(cudaGetLastError(), "cudaMemcpy(table)");
+		cudaFree(d);
+		return nullptr;
+	}
+	(void)st;
+	g_tables[key] = d;
+	return d;
+}
+
+template <int LOG2M>
+static void build_twiddles(std::vector<float2> &tw) {
+	using S = FftSched<LOG2M>;
+	tw.assign(S::TW_TOTAL, make_float2(0.f, 0.f));
+	for (int p = 1; p < S::NP; p++) {
+		const int r = 1 << S::bits(p), ns = 1 << S::ns_log2(p);
+		for (int t = 1; t < r; t++)
+			for (int k = 0; k < ns; k++) {
+				const double ang = -2.0 * M_PI * (double)t * (double)k / ((double)ns * (double)r);
+				tw[S::tw_offset(p) + (t - 1) * ns + k] = make_float2((float)cos(ang), (float)sin(ang));
+			}
+	}
+	for (int k = 0; k <= S::M / 2; k++) {
+		const double ang = -M_PI * (double)k / (double)S::M;
+		tw[S::TW_SPLIT_OFFSET + k] = make_float2((float)cos(ang), (float)sin(ang));
+	}
+}
+
+const float2 *fft_twiddles(int device, int log2m, cudaStream_t st) {
+	std::lock_guard<std::mutex> lk(g_mu);
+	TableKey key{device, 1, log2m, 0};
+	auto it = g_tables.find(key);
+	if (it != g_tables.end()) return (const float2 *)it->second;
+	std::vector<float2> tw;
+	switch (log2m) {
+	case 4: build_twiddles<4>(tw); break;
+	case 5: build_twiddles<5>(tw); break;
+	case 6: build_twiddles<6>(tw); break;
+	case 7: build_twiddles<7>(tw); break;
+	case 8: build_twiddles<8>(tw); break;
+	case 9: build_twiddles<9>(tw); break;
+	case 10: build_twiddles<10>(tw); break;
+	case 11: build_twiddles<11>(tw); break;
+	case 12: build_twiddles<12>(tw); break;
+	case 13: build_twiddles<13>(tw); break;
+	case 14: build_twiddles<14>(tw); break;
+	default: set_error("fft_twiddles: unsupported size"); return nullptr;
+	}
+	return (const float2 *)upload_table(key, tw.data(), tw.size() * sizeof(float2), st);
+}
+
+static uint64_t fnv1a(const void *p, size_t n) {
+	const unsigned char *b = (const unsigned char *)p;
+	uint64_t h = 1469598103934665603ull;
+	for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
+	return h;
+}
+
+const float *device_window(int device, const float *host_window, int n, cudaStream_t st) {
+	std::lock_guard<std::mutex> lk(g_mu);
+	TableKey key{device, 2, n, fnv1a(host_window, (size_t)n * sizeof(float))};
+	auto it = g_tables.find(key);
+	if (it != g_tables.end()) return (const float *)it->second;
+	return (const float *)upload_table(key, host_window, (size_t)n * sizeof(float), st);
+}
+
+int sinc_tables(int device, int nt, cudaStream_t st, SincTables *out) {
+	std::lock_guard<std::mutex> lk(g_mu);
+	const int padded = ((2 * nt + 15) / 16) * 16 + 16;
+	TableKey key{device, 3, nt, 0};
+	auto it = g_tables.find(key);
+	const float *base;
+	if (it != g_tables.end()) {
+		base = (const float *)it->second;
+	} else {
+		// np.hanning(2nt+1) rounded to float32 (util/resampling.py:24,36), then /pi and the
+		// alternating sign of sin(pi (d - s)) folded in, in float64, rounded once
+		std::vector<float> tab(2 * (size_t)padded, 0.f);
+		const int mm = 2 * nt + 1;
+		for (int k = 0; k < 2 * nt; k++) {
+			const double nn = (double)(1 - mm + 2 * k);
+			const float h = (float)(0.5 + 0.5 * cos(M_PI * nn / (double)(mm - 1)));
+			const int d = k - nt;
+			const double sign = ((d + 1) & 1) ? -1.0 : 1.0;
+			tab[k] = (float)(sign * (double)h / M_PI);
+			tab[padded + k] = (float)((double)h / M_PI);
+		}
+		base = (const float *)upload_table(key, tab.data(), tab.size() * sizeof(float), st);
+		if (!base) return PAR_ECUDA;
+	}
+	out->c = base;
+	out->hp = base + padded;
+	out->padded = padded;
+	return PAR_OK;
+}
+
+// ---- helpers ------------------------------------------------------------------------------------
+static int use_device(int device) {
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n <= 0) {
+		cudaGetLastError();
+		set_error("no usable CUDA device (libpar_b200 has no CPU fallback)");
+		return PAR_ECUDA;
+	}
+	if (device < 0 || device >= n) { set_error("device index out of range"); return PAR_EINVAL; }
+	PAR_CUDA(cudaSetDevice(device));
+	return PAR_OK;
+}
+
+// RAII device buffer from the stream-ordered pool
+struct DevBuf {
+	void *p = nullptr;
+	cudaStream_t st;
+	explicit DevBuf(cudaStream_t s) : st(s) {}
+	int alloc(size_t bytes) {
+		if (bytes == 0) bytes = 16;
+		PAR_CUDA(cudaMallocAsync(&p, bytes, st));
+		return PAR_OK;
+	}
+	~DevBuf() { if (p) cudaFreeAsync(p, st); }
+	template <class T> T *as() { return (T *)p; }
+};
+
+struct EventTimer {
+	cudaEvent_t a = nullptr, b = nullptr;
+	cudaStream_t st;
+	explicit EventTimer(cudaStream_t s) : st(s) {
+		cudaEventCreate(&a);
+		cudaEventCreate(&b);
+	}
+	void start() { cudaEventRecord(a, st); }
+	void stop() { cudaEventRecord(b, st); }
+	void finish() {
+		float ms = 0.f;
+		if (cudaEventSynchronize(b) == cudaSuccess && cudaEventElapsedTime(&ms, a, b) == cudaSuccess) g_last_ms = ms;
+	}
+	~EventTimer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+};
+
+// strided host channel <-> planar device copies
+static int h2d_channels(float *dst, int64_t dst_ch_stride, const float *src, int64_t n, int64_t stride,
+                        int n_ch, int64_t ch_stride, cudaStream_t st) {
+	for (int c = 0; c < n_ch; c++) {
+		if (stride == 1) {
+			PAR_CUDA(cudaMemcpyAsync(dst + c * dst_ch_stride, src + c * ch_stride, n * sizeof(float),
+			                         cudaMemcpyHostToDevice, st));
+		} else {
+			PAR_CUDA(cudaMemcpy2DAsync(dst + c * dst_ch_stride, sizeof(float), src + c * ch_stride,
+			                           stride * sizeof(float), sizeof(float), n, cudaMemcpyHostToDevice, st));
+		}
+	}
+	return PAR_OK;
+}
+static int d2h_channels(float *dst, int64_t n, int64_t stride, int n_ch, int64_t ch_stride, const float *src,
+                        int64_t src_ch_stride, cudaStream_t st) {
+	for (int c = 0; c < n_ch; c++) {
+		if (stride == 1) {
+			PAR_CUDA(cudaMemcpyAsync(dst + c * ch_stride, src + c * src_ch_stride, n * sizeof(float),
+			                         cudaMemcpyDeviceToHost, st));
+		} else {
+			PAR_CUDA(cudaMemcpy2DAsync(dst + c * ch_stride, stride * sizeof(float), src + c * src_ch_stride,
+			                           sizeof(float), sizeof(float), n, cudaMemcpyDeviceToHost, st));
+		}
+	}
+	return PAR_OK;
+}
+
+}  // namespace par
+
+using namespace par;
+
+extern "C" {
+
+PAR_API const char *par_last_error(void) { return g_err.c_str(); }
+PAR_API const char *par_version(void) { return "par_b200 0.1 (sm_100a)"; }
+PAR_API int par_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n;
+}
+PAR_API int64_t par_kernel_launch_count(void) { return g_launches.load(); }
+PAR_API double par_last_kernel_ms(void) { return g_last_ms; }
+
+PAR_API void *par_host_alloc(int64_t bytes) {
+	void *p = nullptr;
+	if (bytes <= 0) bytes = 16;
+	if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocPortable) != cudaSuccess) {
+		cuda_fail(cudaGetLastError(), "cudaHostAlloc");
+		return nullptr;
+	}
+	return p;
+}
+PAR_API void par_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+PAR_API int64_t par_stft_num_frames(int64_t n, int n_fft, int hop) {
+	if (n < 1 || n_fft < 2 || hop < 1) return 0;
+	return (n + 2 * (int64_t)(n_fft / 2) - n_fft) / hop + 1;
+}
+
+PAR_API int par_stft_f32(const float *x, int64_t n, int64_t x_stride, int n_ch, int64_t x_ch_stride,
+                 int n_fft, int hop, int zeropad, const float *window,
+                 void *out, int64_t out_pitch, int64_t out_ch_stride,
+                 unsigned flags, int device, void *stream) {
+	if (!x || !out || !window) { set_error("stft: null pointer"); return PAR_EINVAL; }
+	if (n < 1 || n_ch < 1 || n_fft < 2 || hop < 1 || zeropad < 1 || x_stride < 1) {
+		set_error("stft: bad size argument");
+		return PAR_EINVAL;
+	}
+	const int64_t F = (int64_t)n_fft * zeropad / 2 + 1;
+	const int64_t T = par_stft_num_frames(n, n_fft, hop);
+	if (out_pitch < F) { set_error("stft: out_pitch smaller than the number of bins"); return PAR_EINVAL; }
+	int rc = use_device(device);
+	if (rc != PAR_OK) return rc;
+	cudaStream_t st = (cudaStream_t)stream;
+	const float *dwin = device_window(device, window, n_fft, st);
+	if (!dwin) return PAR_ECUDA;
+	const bool mag = flags & PAR_OUT_MAGNITUDE;
+	StftArgs a;
+	a.n = n; a.n_ch = n_ch; a.n_fft = n_fft; a.hop = hop; a.zeropad = zeropad; a.n_frames = T;
+	a.window = dwin; a.magnitude = mag ? 1 : 0;
+	if (flags & PAR_DEVICE_PTRS) {
+		a.x = x; a.x_stride = x_stride; a.x_ch_stride = x_ch_stride;
+		a.out = out; a.out_pitch = out_pitch; a.out_ch_stride = out_ch_stride;
+		return launch_stft(a, device, st);
+	}
+	// host pointers: stage planar input, run, copy the rows back
+	const size_t esz = mag ? sizeof(float) : sizeof(float2);
+	const int64_t n_al = (n + 3) & ~(int64_t)3;
+	DevBuf dx(st), dout(st);
+	if ((rc = dx.alloc((size_t)n_al * n_ch * sizeof(float))) != PAR_OK) return rc;
+	if ((rc = dout.alloc((size_t)T * F * n_ch * esz)) != PAR_OK) return rc;
+	if ((rc = h2d_channels(dx.as<float>(), n_al, x, n, x_stride, n_ch, x_ch_stride, st)) != PAR_OK) return rc;
+	a.x = dx.as<float>(); a.x_stride = 1; a.x_ch_stride = n_al;
+	a.out = dout.p; a.out_pitch = F; a.out_ch_stride = T * F;
+	EventTimer tm(st);
+	tm.start();
+	if ((rc = launch_stft(a, device, st)) != PAR_OK) return rc;
+	tm.stop();
+	for (int c = 0; c < n_ch; c++) {
+		char *dst = (char *)out + (size_t)c * out_ch_stride * esz;
+		const char *src = (const char *)dout.p + (size_t)c * T * F * esz;
+		if (out_pitch == F) {
+			PAR_CUDA(cudaMemcpyAsync(dst, src, (size_t)T * F * esz, cudaMemcpyDeviceToHost, st));
+		} else {
+			PAR_CUDA(cudaMemcpy2DAsync(dst, out_pitch * esz, src, F * esz, F * esz, T, cudaMemcpyDeviceToHost, st));
+		}
+	}
+	PAR_CUDA(cudaStreamSynchronize(st));
+	tm.finish();
+	return PAR_OK;
+}
+
+PAR_API int par_istft_f32(const void *S, int n_fft, int64_t n_frames, int64_t s_pitch, int n_ch,
+                  int64_t s_ch_stride, int hop, const float *window, int64_t start,
+                  int64_t length, float *y, int64_t y_stride, int64_t y_ch_stride,
+                  unsigned flags, int device, void *stream) {
+	if (!S || !y || !window) { set_error("istft: null pointer"); return PAR_EINVAL; }
+	const int64_t F = n_fft / 2 + 1;
+	if (n_fft < 2 || (n_fft & 1) || n_frames < 1 || n_ch < 1 || hop < 1 || s_pitch < F || start < 0 ||
+	    length < 0 || y_stride < 1) {
+		set_error("istft: bad size argument");
+		return PAR_EINVAL;
+	}
+	int rc = use_device(device);
+	if (rc != PAR_OK) return rc;
+	cudaStream_t st = (cudaStream_t)stream;
+	const float *dwin = device_window(device, window, n_fft, st);
+	if (!dwin) return PAR_ECUDA;
+	DevBuf frames(st);
+	if ((rc = frames.alloc((size_t)n_ch * n_frames * n_fft * sizeof(float))) != PAR_OK) return rc;
+	IstftArgs a;
+	a.n_fft = n_fft; a.n_frames = n_frames; a.n_ch = n_ch; a.hop = hop; a.window = dwin;
+	a.start = start; a.length = length; a.frames = frames.as<float>();
+	if (flags & PAR_DEVICE_PTRS) {
+		a.S = (const float2 *)S; a.s_pitch = s_pitch; a.s_ch_stride = s_ch_stride;
+		a.y = y; a.y_stride = y_stride; a.y_ch_stride = y_ch_stride;
+		return launch_istft(a, device, st);
+	}
+	DevBuf ds(st), dy(st);
+	if ((rc = ds.alloc((size_t)n_ch * n_frames * F * sizeof(float2))) != PAR_OK) return rc;
+	if ((rc = dy.alloc((size_t)n_ch * (length > 0 ? length : 1) * sizeof(float))) != PAR_OK) return rc;
+	for (int c = 0; c < n_ch; c++) {
+		const char *src = (const char *)S + (size_t)c * s_ch_stride * sizeof(float2);
+		char *dst = (char *)ds.p + (size_t)c * n_frames * F * sizeof(float2);
+		PAR_CUDA(cudaMemcpy2DAsync(dst, F * sizeof(float2), src, s_pitch * sizeof(float2), F * sizeof(float2),
+		                           n_frames, cudaMemcpyHostToDevice, st));
+	}
+	a.S = ds.as<float2>(); a.s_pitch = F; a.s_ch_stride = n_frames * F;
+	a.y = dy.as<float>(); a.y_stride = 1; a.y_ch_stride = length;
+	EventTimer tm(st);
+	tm.start();
+	if ((rc = launch_istft(a, device, st)) != PAR_OK) return rc;
+	tm.stop();
+	if (length > 0 && (rc = d2h_channels(y, length, y_stride, n_ch, y_ch_stride, dy.as<float>(), length, st)) != PAR_OK)
+		return rc;
+	PAR_CUDA(cudaStreamSynchronize(st));
+	tm.finish();
+	return PAR_OK;
+}
+
+PAR_API int par_speed_segments(const double *sampletimes, const double *speeds, int64_t k,
+                       int64_t *seg_n, int64_t *total) {
+	if (!sampletimes || !speeds || k < 2 || !seg_n) { set_error("speed_segments: bad argument"); return PAR_EINVAL; }
+	// util/resampling.py:111-118; this translation unit is compiled with -ffp-contract=off
+	volatile double err = 0.0;
+	int64_t sum = 0;
+	for (int64_t i = 0; i + 1 < k; i++) {
+		volatile double period = sampletimes[i + 1] - sampletimes[i];
+		volatile double mean = (speeds[i] + speeds[i + 1]) / 2.0;
+		volatile double prod = period * mean;
+		volatile double inerr = prod + err;
+		const double nr = nearbyint(inerr);       // Python round(): half to even
+		if (!(fabs(nr) < 9.0e15)) { set_error("speed_segments: non-finite segment length"); return PAR_EINVAL; }
+		const int64_t n = (int64_t)nr;
+		err = inerr - (double)n;
+		seg_n[i] = n;
+		if (n > 0) sum += n;
+	}
+	if (total) *total = sum;
+	return PAR_OK;
+}
+
+PAR_API int par_speed_to_pos_f64(const double *sampletimes, const double *speeds, int64_t k,
+                         double num_input_samples, double *pos, int64_t cap, int64_t *m,
+                         unsigned flags, int device, void *stream) {
+	if (!sampletimes || !speeds || k < 2 || !m || (!pos && cap > 0)) {
+		set_error("speed_to_pos: bad argument");
+		return PAR_EINVAL;
+	}
+	int rc = use_device(device);
+	if (rc != PAR_OK) return rc;
+	cudaStream_t st = (cudaStream_t)stream;
+	const int64_t n_seg = k - 1;
+	std::vector<int64_t> seg_n(n_seg), seg_start(n_seg);
+	int64_t total = 0;
+	if ((rc = par_speed_segments(sampletimes, speeds, k, seg_n.data(), &total)) != PAR_OK) return rc;
+	int64_t o = 0;
+	for (int64_t i = 0; i < n_seg; i++) { seg_start[i] = o; if (seg_n[i] > 0) o += seg_n[i]; }
+
+	DevBuf d_sp(st), d_n(st), d_sum(st), d_start(st), d_off(st);
+	if ((rc = d_sp.alloc(k * sizeof(double))) != PAR_OK) return rc;
+	if ((rc = d_n.alloc(n_seg * sizeof(int64_t))) != PAR_OK) return rc;
+	if ((rc = d_sum.alloc(n_seg * sizeof(double))) != PAR_OK) return rc;
+	if ((rc = d_start.alloc(n_seg * sizeof(int64_t))) != PAR_OK) return rc;
+	if ((rc = d_off.alloc(n_seg * sizeof(double))) != PAR_OK) return rc;
+	PAR_CUDA(cudaMemcpyAsync(d_sp.p, speeds, k * sizeof(double), cudaMemcpyHostToDevice, st));
+	PAR_CUDA(cudaMemcpyAsync(d_n.p, seg_n.data(), n_seg * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+	if ((rc = launch_segment_sums(d_sp.as<double>(), d_n.as<int64_t>(), n_seg, d_sum.as<double>(), st)) != PAR_OK)
+		return rc;
+	std::vector<double> sums(n_seg), off(n_seg);
+	PAR_CUDA(cudaMemcpyAsync(sums.data(), d_sum.p, n_seg * sizeof(double), cudaMemcpyDeviceToHost, st));
+	PAR_CUDA(cudaStreamSynchronize(st));
+
+	// serial offset chain + end test (util/resampling.py:125-135)
+	volatile double offset = sampletimes[0];
+	int64_t m_out = total;
+	for (int64_t i = 0; i < n_seg; i++) {
+		off[i] = offset;
+		const int64_t n = seg_n[i];
+		if (n <= 0) continue;                   // the reference raises on an empty block
+		volatile double inv0 = 1.0 / speeds[i];
+		if (n == 1) inv0 = NAN;                 // arange(1)/0 -> nan in the reference
+		volatile double first = inv0 + offset;
+		volatile double last = sums[i] + offset;
+		if (first <= num_input_samples && num_input_samples <= last) {
+			// np.argmin(|sample_at - L|) over this block, first minimum
+			const double ds = speeds[i + 1] - speeds[i];
+			const double nm1 = (double)(n - 1);
+			volatile double acc = 0.0;
+			double best = INFINITY;
+			int64_t besti = 0;
+			for (int64_t j = 0; j < n; j++) {
+				volatile double q = (double)j / nm1;
+				volatile double v = q * ds;
+				v = v + speeds[i];
+				volatile double r = 1.0 / v;
+				acc = acc + r;
+				volatile double p = acc + offset;
+				const double dist = fabs(p - num_input_samples);
+				if (dist < best) { best = dist; besti = j; }
+			}
+			m_out = seg_start[i] + besti;
+			break;
+		}
+		offset = last;
+	}
+	*m = m_out;
+	if (m_out > cap) {
+		set_error("speed_to_pos: output capacity too small");
+		return PAR_ECAPACITY;
+	}
+	if (m_out == 0) return PAR_OK;
+	PAR_CUDA(cudaMemcpyAsync(d_start.p, seg_start.data(), n_seg * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+	PAR_CUDA(cudaMemcpyAsync(d_off.p, off.data(), n_seg * sizeof(double), cudaMemcpyHostToDevice, st));
+	if (flags & PAR_DEVICE_PTRS) {
+		rc = launch_expand_positions(d_sp.as<double>(), d_n.as<int64_t>(), d_start.as<int64_t>(), d_off.as<double>(),
+		                             n_seg, pos, m_out, st);
+		if (rc != PAR_OK) return rc;
+		PAR_CUDA(cudaStreamSynchronize(st));  // host vectors above must outlive the async copies
+		return PAR_OK;
+	}
+	DevBuf d_pos(st);
+	if ((rc = d_pos.alloc(m_out * sizeof(double))) != PAR_OK) return rc;
+	rc = launch_expand_positions(d_sp.as<double>(), d_n.as<int64_t>(), d_start.as<int64_t>(), d_off.as<double>(),
+	                             n_seg, d_pos.as<double>(), m_out, st);
+	if (rc != PAR_OK) return rc;
+	PAR_CUDA(cudaMemcpyAsync(pos, d_pos.p, m_out * sizeof(double), cudaMemcpyDeviceToHost, st));
+	PAR_CUDA(cudaStreamSynchronize(st));
+	return PAR_OK;
+}
+
+static int resample_common(bool sinc, const double *pos, int64_t m, const float *signal, int64_t n_in,
+                           int64_t sig_stride, int n_ch, int64_t sig_ch_stride, int nt,
+                           float *out, int64_t out_stride, int64_t out_ch_stride,
+                           unsigned flags, int device, void *stream) {
+	if (m < 0 || n_in < 0 || n_ch < 1 || sig_stride < 1 || out_stride < 1 || (sinc && (nt < 1 || nt > 512))) {
+		set_error("resample: bad size argument");
+		return PAR_EINVAL;
+	}
+	if (m > 0 && (!pos || !out)) { set_error("resample: null pointer"); return PAR_EINVAL; }
+	if (n_in > 0 && !signal) { set_error("resample: null signal"); return PAR_EINVAL; }
+	int rc = use_device(device);
+	if (rc != PAR_OK) return rc;
+	if (m == 0) return PAR_OK;
+	cudaStream_t st = (cudaStream_t)stream;
+	SincArgs a;
+	a.m = m; a.n_in = n_in; a.n_ch = n_ch; a.nt = nt;
+	a.aligned_edges = (flags & PAR_SINC_ALIGNED_EDGES) ? 1 : 0;
+	if (flags & PAR_DEVICE_PTRS) {
+		a.pos = pos; a.signal = signal; a.sig_stride = sig_stride; a.sig_ch_stride = sig_ch_stride;
+		a.out = out; a.out_stride = out_stride; a.out_ch_stride = out_ch_stride;
+		return sinc ? launch_sinc(a, device, st) : launch_linear(a, device, st);
+	}
+	const int64_t n_al = ((n_in > 0 ? n_in : 1) + 3) & ~(int64_t)3;
+	DevBuf dpos(st), dsig(st), dout(st);
+	if ((rc = dpos.alloc(m * sizeof(double))) != PAR_OK) return rc;
+	if ((rc = dsig.alloc((size_t)n_al * n_ch * sizeof(float))) != PAR_OK) return rc;
+	if ((rc = dout.alloc((size_t)m * n_ch * sizeof(float))) != PAR_OK) return rc;
+	PAR_CUDA(cudaMemcpyAsync(dpos.p, pos, m * sizeof(double), cudaMemcpyHostToDevice, st));
+	if (n_in > 0 &&
+	    (rc = h2d_channels(dsig.as<float>(), n_al, signal, n_in, sig_stride, n_ch, sig_ch_stride, st)) != PAR_OK)
+		return rc;
+	a.pos = dpos.as<double>(); a.signal = dsig.as<float>(); a.sig_stride = 1; a.sig_ch_stride = n_al;
+	a.out = dout.as<float>(); a.out_stride = 1; a.out_ch_stride = m;
+	EventTimer tm(st);
+	tm.start();
+	if ((rc = sinc ? launch_sinc(a, device, st) : launch_linear(a, device, st)) != PAR_OK) return rc;
+	tm.stop();
+	if ((rc = d2h_channels(out, m, out_stride, n_ch, out_ch_stride, dout.as<float>(), m, st)) != PAR_OK) return rc;
+	PAR_CUDA(cudaStreamSynchronize(st));
+	tm.finish();
+	return PAR_OK;
+}
+
+PAR_API int par_sinc_resample_f32(const double *pos, int64_t m, const float *signal, int64_t n_in,
+                          int64_t sig_stride, int n_ch, int64_t sig_ch_stride, int nt,
+                          float *out, int64_t out_stride, int64_t out_ch_stride,
+                          unsigned flags, int device, void *stream) {
+	return resample_common(true, pos, m, signal, n_in, sig_stride, n_ch, sig_ch_stride, nt, out, out_stride,
+	                       out_ch_stride, flags, device, stream);
+}
+
+PAR_API int par_linear_resample_f32(const double *pos, int64_t m, const float *signal, int64_t n_in,
+                            int64_t sig_stride, int n_ch, int64_t sig_ch_stride,
+                            float *out, int64_t out_stride, int64_t out_ch_stride,
+                            unsigned flags, int device, void *stream) {
+	return resample_common(false, pos, m, signal, n_in, sig_stride, n_ch, sig_ch_stride, 1, out, out_stride,
+	                       out_ch_stride, flags, device, stream);
+}
+
+}  // extern "C"

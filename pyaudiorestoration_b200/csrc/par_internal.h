@@ -1,0 +1,78 @@
+// par_internal.h -- shared declarations of libpar_b200 (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace par {
+
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what);   // records the message, returns PAR_ECUDA
+void count_launch(int n = 1);
+int sm_count(int device);
+
+#define PAR_CUDA(call)                                              \
+	do {                                                            \
+		cudaError_t _e = (call);                                    \
+		if (_e != cudaSuccess) return par::cuda_fail(_e, #call);    \
+	} while (0)
+
+// Device-resident constant tables, cached per (device, key); built on the host in float64.
+const float2 *fft_twiddles(int device, int log2m, cudaStream_t st);          // FftSched<log2m> layout
+const float *device_window(int device, const float *host_window, int n, cudaStream_t st);
+// sinc tap coefficients: c[k] = (-1)^(k-nt+1) * hanning(2nt+1)[k] / pi  and  hp[k] = hanning[k] / pi,
+// k = 0 .. 2nt-1, each padded with zeros to a multiple of 16 (+16)
+struct SincTables {
+	const float *c;    // fc == 1 path
+	const float *hp;   // fc < 1 path
+	int padded;        // entries per table
+};
+int sinc_tables(int device, int nt, cudaStream_t st, SincTables *out);
+
+// ---- kernel launchers (all asynchronous on `st`, device pointers only) -----------------------
+struct StftArgs {
+	const float *x;
+	int64_t n, x_stride, x_ch_stride;
+	int n_ch, n_fft, hop, zeropad;
+	int64_t n_frames;
+	const float *window;   // device
+	void *out;
+	int64_t out_pitch, out_ch_stride;
+	int magnitude;
+};
+int launch_stft(const StftArgs &a, int device, cudaStream_t st);
+
+struct IstftArgs {
+	const float2 *S;
+	int n_fft;
+	int64_t n_frames, s_pitch, s_ch_stride;
+	int n_ch, hop;
+	const float *window;   // device
+	int64_t start, length;
+	float *y;
+	int64_t y_stride, y_ch_stride;
+	float *frames;         // device scratch: n_ch * n_frames * n_fft floats
+};
+int launch_istft(const IstftArgs &a, int device, cudaStream_t st);
+
+int launch_segment_sums(const double *speeds_dev, const int64_t *seg_n_dev, int64_t n_seg,
+                        double *sums_dev, cudaStream_t st);
+int launch_expand_positions(const double *speeds_dev, const int64_t *seg_n_dev,
+                            const int64_t *seg_start_dev, const double *seg_offset_dev,
+                            int64_t n_seg, double *pos_dev, int64_t m, cudaStream_t st);
+
+struct SincArgs {
+	const double *pos;
+	int64_t m;
+	const float *signal;
+	int64_t n_in, sig_stride, sig_ch_stride;
+	int n_ch, nt;
+	float *out;
+	int64_t out_stride, out_ch_stride;
+	int aligned_edges;
+};
+int launch_sinc(const SincArgs &a, int device, cudaStream_t st);
+int launch_linear(const SincArgs &a, int device, cudaStream_t st);
+
+}  // namespace par

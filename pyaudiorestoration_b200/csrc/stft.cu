@@ -1,0 +1,180 @@
+// stft.cu -- fused short-time Fourier transform for sm_100a.
+//
+// Replaces, in one kernel, the reference's estimate_and_center (np.pad reflect,
+// util/fourier.py:78-82), segment_array (frame gather * window, zero tail, :160-166), the
+// batched real FFT of pyfftw_rfft2 / np_rfft_pick / torch_rfft2 (:92-157) with its
+// 1/sqrt(n_fft) scaling (:105,:157) and, optionally, to_mag (:23-24).
+//
+// One transform = one frame.  The real frame of length N*Z is packed as M = N*Z/2 complex
+// points z[n] = (w[2n] x[2n], w[2n+1] x[2n+1]) (zeros beyond N), transformed with the Stockham
+// passes of fft_core.cuh, and split into the N*Z/2+1 one-sided bins on the way out.
+// Algorithmic HBM traffic per frame: hop*4 B of new input (overlap re-reads are L1/L2 hits)
+// + (N*Z/2+1)*8 B of output (4 B in magnitude mode).
+#include "fft_core.cuh"
+#include "par_internal.h"
+#include "../../include/par_b200.h"
+
+namespace par {
+
+__device__ __forceinline__ int64_t reflect_index(int64_t i, int64_t n) {
+	// np.pad(mode='reflect') index map, any pad length
+	if (n == 1) return 0;
+	const int64_t period = 2 * (n - 1);
+	i %= period;
+	if (i < 0) i += period;
+	return i < n ? i : period - i;
+}
+
+struct FrameLoad {
+	const float *x;        // channel base
+	int64_t n, stride, base;
+	const float2 *win2;    // window as float2 pairs
+	int half_n;            // N/2: packed elements that carry samples
+	bool fast, valid;
+	__device__ __forceinline__ float2 operator()(int e) const {
+		if (e >= half_n || !valid) return make_float2(0.f, 0.f);
+		const float2 w = __ldg(win2 + e);
+		const int64_t s = base + 2 * (int64_t)e;
+		float a, b;
+		if (fast) {
+			const float2 v = __ldg(reinterpret_cast<const float2 *>(x + s));
+			a = v.x;
+			b = v.y;
+		} else {
+			a = __ldg(x + reflect_index(s, n) * stride);
+			b = __ldg(x + reflect_index(s + 1, n) * stride);
+		}
+		return make_float2(a * w.x, b * w.y);
+	}
+};
+
+template <int LOG2M>
+struct StftCfg {
+	using S = FftSched<LOG2M>;
+	static constexpr bool INPLACE = LOG2M >= 14;
+	static constexpr int BLOCK = S::TPF < 128 ? 128 : S::TPF;
+	static constexpr int FPB = BLOCK / S::TPF;                      // frames per block pass
+	static constexpr int SMEM = FPB * (INPLACE ? 1 : 2) * S::BUF * (int)sizeof(float2);
+};
+
+template <int LOG2M, bool MAG>
+__global__ void __launch_bounds__(StftCfg<LOG2M>::BLOCK)
+stft_kernel(StftArgs a, const float2 *__restrict__ tw, float half_scale) {
+	using S = FftSched<LOG2M>;
+	using C = StftCfg<LOG2M>;
+	extern __shared__ float2 smem[];
+	const int slot = threadIdx.x / S::TPF;
+	const int tid = threadIdx.x % S::TPF;
+	float2 *buf0 = smem + slot * (C::INPLACE ? 1 : 2) * S::BUF;
+	float2 *buf1 = C::INPLACE ? buf0 : buf0 + S::BUF;
+	const int64_t total = (int64_t)a.n_ch * a.n_frames;
+	const int64_t groups = (total + C::FPB - 1) / C::FPB;
+	const int half_n = a.n_fft >> 1;
+
+	for (int64_t g = blockIdx.x; g < groups; g += gridDim.x) {
+		const int64_t f = g * C::FPB + slot;
+		const bool valid = f < total;
+		const int64_t ch = valid ? f / a.n_frames : 0;
+		const int64_t t = valid ? f - ch * a.n_frames : 0;
+		FrameLoad ld;
+		ld.x = a.x + ch * a.x_ch_stride;
+		ld.n = a.n;
+		ld.stride = a.x_stride;
+		ld.base = t * a.hop - half_n;
+		ld.win2 = reinterpret_cast<const float2 *>(a.window);
+		ld.half_n = half_n;
+		ld.valid = valid;
+		ld.fast = a.x_stride == 1 && ld.base >= 0 && ld.base + a.n_fft <= a.n &&
+		          ((reinterpret_cast<uintptr_t>(ld.x + ld.base) & 7) == 0);
+
+		if (C::INPLACE)
+			stockham_pass_inplace<LOG2M, 0, false>(tid, ld, buf0, tw);
+		else
+			stockham_pass<LOG2M, 0, false>(tid, ld, buf0, tw);
+		float2 *res = RunPasses<LOG2M, false, C::INPLACE, 1>::run(tid, buf0, buf1, tw);
+		__syncthreads();
+
+		if (valid) {
+			const int64_t row = ch * a.out_ch_stride + t * a.out_pitch;
+			const float2 *tws = tw + S::TW_SPLIT_OFFSET;
+			for (int k = tid; k <= S::M / 2; k += S::TPF) {
+				const float2 zk = res[pad16(k)];
+				const float2 zm = res[pad16((S::M - k) & (S::M - 1))];
+				const float2 w = __ldg(tws + k);
+				// 2E = zk + conj(zm); 2O = -i (zk - conj(zm)); X[k] = E + W^k O; X[M-k] = conj(E - W^k O)
+				const float ex = zk.x + zm.x, ey = zk.y - zm.y;
+				const float ox = zk.y + zm.y, oy = zm.x - zk.x;
+				const float2 wo = cmul(make_float2(ox, oy), w);
+				const float2 xa = make_float2((ex + wo.x) * half_scale, (ey + wo.y) * half_scale);
+				const float2 xb = make_float2((ex - wo.x) * half_scale, (wo.y - ey) * half_scale);
+				if (MAG) {
+					float *o = reinterpret_cast<float *>(a.out) + row;
+					o[k] = sqrtf(fmaf(xa.x, xa.x, xa.y * xa.y)) + 1e-7f;
+					if (k != S::M - k) o[S::M - k] = sqrtf(fmaf(xb.x, xb.x, xb.y * xb.y)) + 1e-7f;
+				} else {
+					float2 *o = reinterpret_cast<float2 *>(a.out) + row;
+					o[k] = xa;
+					if (k != S::M - k) o[S::M - k] = xb;
+				}
+			}
+		}
+		__syncthreads();
+	}
+}
+
+template <int LOG2M, bool MAG>
+static int launch_one(const StftArgs &a, int device, cudaStream_t st) {
+	using C = StftCfg<LOG2M>;
+	const float2 *tw = fft_twiddles(device, LOG2M, st);
+	if (!tw) return PAR_ECUDA;
+	auto kern = stft_kernel<LOG2M, MAG>;
+	static thread_local int configured_dev[64] = {0};
+	(void)configured_dev;
+	PAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+	int occ = 0;
+	PAR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::BLOCK, C::SMEM));
+	if (occ < 1) occ = 1;
+	const int64_t total = (int64_t)a.n_ch * a.n_frames;
+	const int64_t groups = (total + C::FPB - 1) / C::FPB;
+	int64_t grid = (int64_t)occ * sm_count(device);
+	if (grid > groups) grid = groups;
+	if (grid < 1) return PAR_OK;
+	const float half_scale = (float)(0.5 / sqrt((double)a.n_fft));
+	kern<<<(unsigned)grid, C::BLOCK, C::SMEM, st>>>(a, tw, half_scale);
+	count_launch();
+	PAR_CUDA(cudaGetLastError());
+	return PAR_OK;
+}
+
+template <bool MAG>
+static int dispatch(const StftArgs &a, int log2m, int device, cudaStream_t st) {
+	switch (log2m) {
+	case 4: return launch_one<4, MAG>(a, device, st);
+	case 5: return launch_one<5, MAG>(a, device, st);
+	case 6: return launch_one<6, MAG>(a, device, st);
+	case 7: return launch_one<7, MAG>(a, device, st);
+	case 8: return launch_one<8, MAG>(a, device, st);
+	case 9: return launch_one<9, MAG>(a, device, st);
+	case 10: return launch_one<10, MAG>(a, device, st);
+	case 11: return launch_one<11, MAG>(a, device, st);
+	case 12: return launch_one<12, MAG>(a, device, st);
+	case 13: return launch_one<13, MAG>(a, device, st);
+	case 14: return launch_one<14, MAG>(a, device, st);
+	}
+	set_error("stft: n_fft*zeropad must be a power of two in [32, 32768]");
+	return PAR_EUNSUPPORTED;
+}
+
+int launch_stft(const StftArgs &a, int device, cudaStream_t st) {
+	const int64_t nz = (int64_t)a.n_fft * a.zeropad;
+	int log2m = -1;
+	for (int b = 4; b <= 14; b++)
+		if (nz == (int64_t)2 << b) log2m = b;
+	if (log2m < 0 || (a.n_fft & 1)) {
+		set_error("stft: n_fft*zeropad must be a power of two in [32, 32768] (n_fft even)");
+		return PAR_EUNSUPPORTED;
+	}
+	return a.magnitude ? dispatch<true>(a, log2m, device, st) : dispatch<false>(a, log2m, device, st);
+}
+
+}  // namespace par
