@@ -112,6 +112,7 @@ struct SampleSetup {
 	int koff;          // weight index of tap 0 (0 unless PAR_SINC_ALIGNED_EDGES at the start edge)
 	float s;           // fractional shift p - round(p), never exactly 0
 	bool lowpass;      // fc < 1
+	float fc;          // fc rounded to float32 (centre tap only)
 	uint64_t f_fx;     // fc in units of 2^-63 half-turns
 	int64_t s_fx;      // fc * s in the same units
 };
@@ -140,7 +141,12 @@ struct BlockWeights {
 		for (int j = 0; j < 16; j++) {
 			const float q = far ? base + (float)j : (float)(d0 + j) - su.s;
 			float num = coef[j];
-			if (LOWPASS) num *= fmaf(sa, cj[j], ca * sj[j]);
+			if (LOWPASS) {
+				// centre tap (|q| <= 0.5): the fixed-point angle has ABSOLUTE accuracy only, but the
+				// weight sin(pi fc q) / q needs RELATIVE accuracy as q -> 0
+				if (d0 == -j) num *= sinpif(su.fc * q);
+				else num *= fmaf(sa, cj[j], ca * sj[j]);
+			}
 			w[j] = num * rcp_approx(q);
 		}
 	}
@@ -211,7 +217,7 @@ sinc_kernel(SincArgs a, const float *__restrict__ ctab, const float *__restrict_
 
 		// ---- per-sample setup in float64 (util/resampling.py:67-84) ----
 		SampleSetup su;
-		su.lower = 0; su.cnt = 0; su.koff = 0; su.s = 1e-30f; su.lowpass = false; su.f_fx = 0; su.s_fx = 0;
+		su.lower = 0; su.cnt = 0; su.koff = 0; su.s = 1e-30f; su.lowpass = false; su.fc = 1.f; su.f_fx = 0; su.s_fx = 0;
 		long long lo = LLONG_MAX, hi = LLONG_MIN;
 		if (live) {
 			const double p = a.pos[i];
@@ -236,6 +242,7 @@ sinc_kernel(SincArgs a, const float *__restrict__ ctab, const float *__restrict_
 			su.s = s;
 			su.lowpass = fc < 1.0;
 			if (su.lowpass) {
+				su.fc = (float)fc;
 				su.f_fx = __double2ull_rn(fc * 9223372036854775808.0);
 				su.s_fx = __double2ll_rn(fc * sd * 9223372036854775808.0);
 			}

@@ -1,0 +1,418 @@
+"""GPU parity tests: the sm_100a kernels, called through the C ABI of libpar_b200.so (via the
+Python mirror of the reference's module surface, and directly with device pointers), against the
+CPU oracle on the committed golden inputs and on seeded synthetic inputs.
+
+Bars (BASELINE.json north_star, SURVEY.md 8c "parity metric"):
+  * float results: ||a-b||_2 / ||b||_2 <= 1e-6 per frame / per channel and
+    max|a-b| / max|b| <= 1e-6 against the float64 oracle;
+  * integer / index results and the float64 read positions: identical.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import oracle_np as onp
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def par():
+    import pyaudiorestoration_b200 as p
+    from pyaudiorestoration_b200 import _lib
+    if not os.path.exists(p.library_path()):
+        p.build()
+    _lib.require_device()
+    return p
+
+
+@pytest.fixture(scope="module")
+def fourier(par):
+    from pyaudiorestoration_b200.util import fourier
+    return fourier
+
+
+@pytest.fixture(scope="module")
+def resampling(par):
+    from pyaudiorestoration_b200.util import resampling
+    return resampling
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+def rel_l2(a, b, axis=None):
+    num = np.sqrt(np.sum(np.abs(a - b) ** 2, axis=axis))
+    den = np.maximum(np.sqrt(np.sum(np.abs(b) ** 2, axis=axis)), 1e-300)
+    return num / den
+
+
+def rel_max(a, b):
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+def synth(n, seed, sr=96000.0):
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) / sr
+    x = 0.25 * np.sin(2 * np.pi * 1000.0 * t) + 0.1 * np.sin(2 * np.pi * (sr / 4.3) * t) \
+        + 0.05 * rng.standard_normal(n)
+    return x.astype(np.float32)
+
+
+def wow_curve(duration, sr, hop, depth=0.01, freq=0.5556):
+    k = int(duration * sr / hop)
+    times = np.linspace(0, duration, k)
+    return np.stack((times, 1 + depth * np.sin(2 * np.pi * freq * times)), -1)
+
+
+# ----------------------------------------------------------------------------------------- STFT
+def _check_stft(s, x, n_fft, step, window, zp):
+    truth = onp.stft_f64(x, n_fft, step, window, zp).T          # (F, T) complex128
+    assert s.shape == truth.shape
+    assert s.dtype == np.complex64
+    per_frame = rel_l2(s.astype(np.complex128), truth, axis=0)
+    scale = np.sqrt(np.mean(np.abs(truth) ** 2))
+    # frames that are (numerically) silent carry no relative information
+    live = np.sqrt(np.mean(np.abs(truth) ** 2, axis=0)) > 1e-6 * scale
+    assert np.all(per_frame[live] <= TOL), float(per_frame[live].max())
+    assert rel_max(s, truth) <= TOL
+
+
+def test_stft_golden_cases(golden_dir, fourier):
+    z = _load(golden_dir, "stft")
+    names = sorted(k[:-6] for k in z.files if k.endswith("__meta"))
+    assert len(names) >= 7
+    for name in names:
+        n_fft, step, zp = (int(v) for v in z[name + "__meta"])
+        window = str(z[name + "__window"])
+        x = z[name + "__x"]
+        s = fourier.stft(x, n_fft, step, window, zp)
+        _check_stft(s, x, n_fft, step, window, zp)
+        # and against the reference's own float32 numpy back-end output
+        ref = z[name + "__S"]
+        assert s.shape == ref.shape
+        assert rel_l2(s, ref) <= 2 * TOL, name
+        assert s.flags.f_contiguous
+
+
+def test_stft_strided_column_view(golden_dir, fourier):
+    z = _load(golden_dir, "stft")
+    inter = z["interleaved__x"]
+    s = fourier.stft(inter[:, 1], 1024, 256)
+    _check_stft(s, np.ascontiguousarray(inter[:, 1]), 1024, 256, "blackmanharris", 1)
+
+
+@pytest.mark.parametrize("n_fft,hop", [(32, 8), (64, 16), (128, 32), (256, 64), (512, 32), (1024, 256),
+                                       (2048, 512), (4096, 1024), (8192, 2048), (16384, 4096),
+                                       (32768, 8192), (4096, 1000), (4096, 4096), (1024, 3000)])
+def test_stft_sizes(fourier, n_fft, hop):
+    x = synth(max(5 * n_fft + 123, 20000), n_fft + hop)
+    s = fourier.stft(x, n_fft, hop)
+    _check_stft(s, x, n_fft, hop, "blackmanharris", 1)
+
+
+@pytest.mark.parametrize("n_fft,hop,zp", [(256, 64, 4), (1024, 256, 2), (2048, 512, 16), (64, 16, 8)])
+def test_stft_zeropad(fourier, n_fft, hop, zp):
+    x = synth(9000, 31 + zp)
+    s = fourier.stft(x, n_fft, hop, "hann", zp)
+    _check_stft(s, x, n_fft, hop, "hann", zp)
+
+
+def test_stft_short_and_edge_inputs(fourier):
+    # shorter than the window but longer than the reflect pad
+    for n, n_fft, hop in [(700, 1024, 256), (513, 1024, 1), (2049, 4096, 1024), (17, 32, 8)]:
+        x = synth(n, n)
+        _check_stft(fourier.stft(x, n_fft, hop), x, n_fft, hop, "blackmanharris", 1)
+    with pytest.raises(ValueError):
+        fourier.stft(np.zeros((10, 2), np.float32))
+    # float64 / int16 inputs are accepted and computed in float32 like the reference's torch path
+    x = synth(5000, 3)
+    s64 = fourier.stft(x.astype(np.float64), 512, 128)
+    assert np.array_equal(s64, fourier.stft(x, 512, 128))
+    # step=None -> n_fft // 2 (util/fourier.py:63)
+    assert fourier.stft(x, 512, None).shape == (257, 5000 // 256 + 1)
+
+
+def test_get_mag_matches_abs_of_stft(fourier):
+    x = synth(50000, 5)
+    mag = fourier.get_mag(x, 4096, 1024)
+    truth = np.abs(onp.stft_f64(x, 4096, 1024).T) + 1e-7
+    assert mag.dtype == np.float32 and mag.shape == truth.shape
+    assert np.all(rel_l2(mag.astype(np.float64), truth, axis=0) <= TOL)
+    assert rel_max(mag, truth) <= TOL
+    mag2 = fourier.get_mag(x, 1024, 256, "hann", 4)
+    truth2 = np.abs(onp.stft_f64(x, 1024, 256, "hann", 4).T) + 1e-7
+    assert rel_max(mag2, truth2) <= TOL
+
+
+def test_stft_linearity_full_size(fourier):
+    """Size-independent property at a BASELINE-sized frame count: STFT(a*x + y) = a*STFT(x) +
+    STFT(y) and Parseval against the time-domain frame energy on sampled frames."""
+    n = 96000 * 60
+    x, y = synth(n, 100), synth(n, 101)
+    a = np.float32(0.37)
+    sx, sy = fourier.stft(x, 4096, 1024), fourier.stft(y, 4096, 1024)
+    sz = fourier.stft(a * x + y, 4096, 1024)
+    assert sx.shape == (2049, n // 1024 + 1)
+    lin = a * sx + sy
+    assert rel_l2(sz, lin) <= 2 * TOL
+    # spot-check frames across the whole length against the oracle
+    win = onp.get_window_f32("blackmanharris", 4096).astype(np.float64)
+    xp = np.pad(x, 2048, mode="reflect").astype(np.float64)
+    for t in (0, 1, 2, 1000, 2811, sx.shape[1] - 2, sx.shape[1] - 1):
+        truth = np.fft.rfft(xp[t * 1024: t * 1024 + 4096] * win) / 64.0
+        assert rel_l2(sx[:, t], truth) <= TOL, t
+
+
+# ----------------------------------------------------------------------------------------- iSTFT
+def test_istft_golden(golden_dir, fourier):
+    z = _load(golden_dir, "istft")
+    for name in ("rt512_32", "rt1024_256", "rt4096_1024"):
+        n_fft, hop, n = (int(v) for v in z[name + "__meta"])
+        s = z[name + "__S"]
+        keep = s.copy()
+        y = fourier.istft(s, hop_length=hop, length=n)
+        assert np.array_equal(s, keep)          # no in-place scaling (reference bug not reproduced)
+        truth = z[name + "__y_from_c128"]       # float64 path of the reference on the same spectrum
+        ref32 = z[name + "__y_from_c64"]
+        assert y.dtype == np.float32 and y.shape == ref32.shape
+        assert rel_l2(y, truth) <= TOL, name
+        assert rel_max(y, truth) <= TOL, name
+        assert rel_max(y, ref32) <= 2 * TOL, name
+        y128 = fourier.istft(s.astype(np.complex128), hop_length=hop, length=n)
+        assert y128.dtype == np.float64
+    s = z["masked__S"]
+    y = fourier.istft(s, hop_length=128)
+    assert y.shape == z["masked__y"].shape
+    assert rel_max(y, z["masked__y"]) <= 2 * TOL
+    assert rel_max(y, onp.istft_ref(s.astype(np.complex128), hop_length=128)) <= TOL
+
+
+@pytest.mark.parametrize("n_fft,hop", [(64, 16), (512, 32), (1024, 256), (4096, 1024), (16384, 4096), (2048, 1024)])
+def test_stft_istft_round_trip(fourier, n_fft, hop):
+    """fix_length -> stft -> istft(length=n) reconstructs the input, the way
+    dropout_healer_gui.py:129-164 chains them."""
+    n = 6 * n_fft + 777
+    x = synth(n, n_fft)
+    ypad = fourier.fix_length(x, n + n_fft // 2)
+    s = fourier.stft(ypad, n_fft, hop)
+    y = fourier.istft(s, hop_length=hop, length=n)
+    assert y.shape == (n,)
+    assert np.max(np.abs(y - x)) <= 1e-6 * np.max(np.abs(x)) * 2
+
+
+def test_istft_length_rules(fourier):
+    x = synth(5000, 77)
+    s = fourier.stft(x, 512, 128)
+    full = fourier.istft(s, hop_length=128)
+    assert full.shape == onp.istft_ref(s, hop_length=128).shape
+    longer = fourier.istft(s, hop_length=128, length=6000)
+    assert longer.shape == (6000,)
+    ref = onp.istft_ref(s.astype(np.complex128), hop_length=128, length=6000)
+    assert rel_max(longer, ref) <= TOL
+    shorter = fourier.istft(s, hop_length=128, length=1000)
+    ref = onp.istft_ref(s.astype(np.complex128), hop_length=128, length=1000)
+    assert rel_max(shorter, ref) <= TOL
+
+
+# ----------------------------------------------------------------------------------------- positions
+def test_speed_to_pos_golden_bit_exact(golden_dir, resampling):
+    z = _load(golden_dir, "positions")
+    for name in ("wow", "ramp"):
+        pos = resampling.speed_to_pos(z[name + "__sampletimes"], z[name + "__speeds"], int(z[name + "__n_in"]))
+        assert pos.dtype == np.float64
+        assert np.array_equal(pos, z[name + "__pos"]), name
+    pos = resampling.speed_to_pos(z["wow5_noend__sampletimes"], z["wow5_noend__speeds"], int(z["wow5_noend__n_in"]))
+    ref = z["wow5_noend__pos"]
+    assert len(pos) < len(ref)
+    assert np.array_equal(pos, ref[: len(pos)])
+
+
+def test_speed_to_pos_matches_oracle_long(resampling):
+    sr, dur = 96000, 20.0
+    curve = wow_curve(dur, sr, 1024)
+    n_in = int(sr * dur)
+    pos = resampling.speed_to_pos(curve[:, 0] * sr, curve[:, 1], n_in)
+    ref = oracle.speed_to_pos_c(curve[:, 0] * sr, curve[:, 1], n_in)
+    assert len(pos) == len(ref)
+    assert np.array_equal(pos, ref)
+    # tuples are accepted (the reference's test_sinc passes tuples, util/resampling.py:271-273)
+    pos = resampling.speed_to_pos((0, 8000), (.5, 2), 8000)
+    assert np.array_equal(pos, oracle.speed_to_pos_c(np.array([0., 8000.]), np.array([.5, 2.]), 8000))
+
+
+# ----------------------------------------------------------------------------------------- resampler
+def _check_sinc(y, pos, x, nt):
+    truth = oracle.sinc_c(pos, x, nt)       # float64 arithmetic, float32 store
+    assert y.dtype == np.float32 and y.shape == truth.shape
+    scale = max(np.max(np.abs(truth)), 1e-30)
+    assert np.max(np.abs(y - truth)) <= TOL * scale, float(np.max(np.abs(y - truth)) / scale)
+    assert rel_l2(y.astype(np.float64), truth.astype(np.float64)) <= TOL
+
+
+def test_sinc_golden(golden_dir, resampling):
+    z = _load(golden_dir, "sinc")
+    checks = [("wow_nt8__y", "wow__pos", "wow__x", 8), ("wow_nt50__y", "wow__pos", "wow__x", 50),
+              ("wow_nt128__y", "wow__pos", "wow__x", 128), ("ramp_nt50__y", "ramp__pos", "ramp__x", 50),
+              ("edges_nt50__y", "edges__pos", "edges__x", 50), ("edges_nt128__y", "edges__pos", "edges__x", 128),
+              ("integer_nt50__y", "integer__pos", "edges__x", 50)]
+    for yk, pk, xk, nt in checks:
+        y = resampling.sinc_wrapper(z[pk], z[xk], 0, nt)
+        ref = z[yk]
+        scale = np.max(np.abs(ref))
+        assert np.max(np.abs(y - ref)) <= TOL * scale, (yk, float(np.max(np.abs(y - ref)) / scale))
+        _check_sinc(y, z[pk], z[xk], nt)
+
+
+@pytest.mark.parametrize("nt", [1, 2, 8, 50, 100, 128, 512])
+def test_sinc_quality_range(resampling, nt):
+    sr = 96000
+    x = synth(sr * 2, nt)
+    curve = wow_curve(2.0, sr, 1024, depth=0.03, freq=2.0)
+    pos = oracle.speed_to_pos_c(curve[:, 0] * sr, curve[:, 1], len(x))
+    y = resampling.sinc_wrapper(pos, x, 0, nt)
+    _check_sinc(y, pos, x, nt)
+
+
+def test_sinc_speed_extremes(resampling):
+    x = synth(40000, 9)
+    for speeds in [(0.5, 2.0), (2.0, 0.5), (0.25, 0.25), (3.9, 3.9), (1.0, 1.0)]:
+        pos = oracle.speed_to_pos_c(np.array([0.0, 30000.0]), np.array(speeds, dtype=np.float64), len(x))
+        y = resampling.sinc_wrapper(pos, x, 0, 50)
+        _check_sinc(y, pos, x, 50)
+
+
+def test_sinc_mt_fills_strided_output(resampling):
+    """sinc_wrapper_mt(output[:, c], sample_at, signal[:, c], 0, NT) exactly as run() calls it
+    (util/resampling.py:227): strided input and output views of interleaved arrays."""
+    sig = np.stack([synth(30000, 1), synth(30000, 2)], axis=1)
+    pos = oracle.speed_to_pos_c(np.array([0.0, 30000.0]), np.array([0.98, 1.03]), 30000)
+    out = np.zeros((len(pos), 2), np.float32)
+    for c in range(2):
+        resampling.sinc_wrapper_mt(out[:, c], pos, sig[:, c], 0, 50)
+        _check_sinc(np.ascontiguousarray(out[:, c]), pos, np.ascontiguousarray(sig[:, c]), 50)
+
+
+def test_sinc_empty_and_degenerate(resampling):
+    x = synth(1000, 4)
+    assert len(resampling.sinc_wrapper(np.zeros(0), x, 0, 8)) == 0
+    # positions far outside the signal give zeros (empty tap slice in the reference)
+    y = resampling.sinc_wrapper(np.array([5000.0, 5001.0, 1e12]), x, 0, 8)
+    assert np.array_equal(y, np.zeros(3, np.float32))
+    # a single position: the reference leaves period_to unbound; fc=1 is used here
+    y1 = resampling.sinc_wrapper(np.array([500.25]), x, 0, 8)
+    assert np.isfinite(y1).all()
+
+
+def test_linear_mode(resampling):
+    x = synth(20000, 6)
+    pos = oracle.speed_to_pos_c(np.array([0.0, 20000.0]), np.array([0.9, 1.2]), 20000)
+    pos = np.concatenate([[-3.0, 0.0, 0.5], pos, [19999.0, 19999.5, 30000.0]])
+    out = resampling.resample_channels(x[:, None], pos, [0], "Linear")
+    ref = onp.linear_resample(pos, x)
+    assert np.array_equal(out[:, 0], ref)
+
+
+# ----------------------------------------------------------------------------------------- run()
+class _Prog:
+    class _Sig:
+        def __init__(self):
+            self.values = []
+
+        def emit(self, v):
+            self.values.append(v)
+
+    def __init__(self):
+        self.notifyProgress = self._Sig()
+
+
+@pytest.mark.parametrize("mode", ["Sinc", "Linear"])
+def test_run_writes_reference_wav(tmp_path, resampling, mode):
+    from pyaudiorestoration_b200.util import io_ops
+    sr = 48000
+    sig = np.stack([synth(sr, 11, sr), synth(sr, 12, sr), synth(sr, 13, sr)], axis=1)
+    curve = wow_curve(1.0, sr, 512, depth=0.02, freq=3.0)
+    prog = _Prog()
+    name = str(tmp_path / "take.wav")
+    ret = resampling.run([name], signal_data=[(sig, sr)], speed_curve=curve, resampling_mode=mode,
+                         sinc_quality=50, use_channels=[0, 2, 7], prog_sig=prog, suffix="_x")
+    assert ret is None
+    out, sr2, ch = io_ops.read_file(str(tmp_path / "take_res_x.wav"))
+    assert sr2 == sr and ch == 2
+    pos = oracle.speed_to_pos_c(curve[:, 0] * sr, curve[:, 1], len(sig))
+    assert out.shape == (len(pos), 2)
+    for o, c in enumerate((0, 2)):
+        x = np.ascontiguousarray(sig[:, c])
+        if mode == "Sinc":
+            _check_sinc(np.ascontiguousarray(out[:, o]), pos, x, 50)
+        else:
+            assert np.array_equal(out[:, o], onp.linear_resample(pos, x))
+    assert prog.notifyProgress.values[0] == 0 and prog.notifyProgress.values[-1] == 100
+
+
+def test_run_lag_curve_and_file_input(tmp_path, resampling):
+    from pyaudiorestoration_b200.util import io_ops
+    sr = 44100
+    sig = np.stack([synth(20000, 21, sr), synth(20000, 22, sr)], axis=1)
+    src = str(tmp_path / "src.wav")
+    io_ops.write_float_wav(src, sig, sr)
+    lag = np.array([[0.0, 0.0], [0.2, 0.001], [0.45, -0.002]])
+    resampling.run([src], lag_curve=lag, resampling_mode="Sinc", sinc_quality=20)
+    out, _, ch = io_ops.read_file(str(tmp_path / "src_res.wav"))
+    pos = onp.lag_to_positions(lag, sr, len(sig))
+    assert ch == 2 and out.shape == (len(pos), 2)
+    _check_sinc(np.ascontiguousarray(out[:, 1]), pos, np.ascontiguousarray(sig[:, 1]), 20)
+
+
+# ----------------------------------------------------------------------------------------- device-pointer ABI
+def test_device_pointer_calls_multichannel(par):
+    """PAR_DEVICE_PTRS entry points on torch-owned device memory and torch's current stream:
+    2-channel planar STFT (complex + magnitude), positions, 2-channel sinc -- the bench path."""
+    import torch
+    from pyaudiorestoration_b200 import _lib
+    L = _lib.lib()
+    dev = torch.device("cuda", _lib.device())
+    sr, dur, n_fft, hop, nt = 96000, 3.0, 4096, 1024, 128
+    n = int(sr * dur)
+    xs = np.stack([synth(n, 1234), synth(n, 1235)])
+    x = torch.from_numpy(xs).to(dev)
+    T = int(L.par_stft_num_frames(n, n_fft, hop))
+    F = n_fft // 2 + 1
+    S = torch.empty((2, T, F), dtype=torch.complex64, device=dev)
+    win = onp.get_window_f32("blackmanharris", n_fft)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    rc = L.par_stft_f32(x.data_ptr(), n, 1, 2, n, n_fft, hop, 1, win.ctypes.data, S.data_ptr(), F, T * F,
+                        _lib.PAR_DEVICE_PTRS, dev.index, stream)
+    _lib.check(rc, "par_stft_f32")
+    M = torch.empty((2, T, F), dtype=torch.float32, device=dev)
+    rc = L.par_stft_f32(x.data_ptr(), n, 1, 2, n, n_fft, hop, 1, win.ctypes.data, M.data_ptr(), F, T * F,
+                        _lib.PAR_DEVICE_PTRS | _lib.PAR_OUT_MAGNITUDE, dev.index, stream)
+    _lib.check(rc, "par_stft_f32 mag")
+    curve = wow_curve(dur, sr, hop)
+    st, sp = np.ascontiguousarray(curve[:, 0] * sr), np.ascontiguousarray(curve[:, 1])
+    ref_pos = oracle.speed_to_pos_c(st, sp, n)
+    pos = torch.empty(len(ref_pos) + 4096, dtype=torch.float64, device=dev)
+    m = np.zeros(1, np.int64)
+    rc = L.par_speed_to_pos_f64(st.ctypes.data, sp.ctypes.data, len(st), float(n), pos.data_ptr(), pos.numel(),
+                                m.ctypes.data, _lib.PAR_DEVICE_PTRS, dev.index, stream)
+    _lib.check(rc, "par_speed_to_pos_f64")
+    m = int(m[0])
+    assert m == len(ref_pos)
+    out = torch.empty((2, m), dtype=torch.float32, device=dev)
+    rc = L.par_sinc_resample_f32(pos.data_ptr(), m, x.data_ptr(), n, 1, 2, n, nt, out.data_ptr(), 1, m,
+                                 _lib.PAR_DEVICE_PTRS, dev.index, stream)
+    _lib.check(rc, "par_sinc_resample_f32")
+    torch.cuda.synchronize(dev)
+    assert np.array_equal(pos[:m].cpu().numpy(), ref_pos)
+    S, M, out = S.cpu().numpy(), M.cpu().numpy(), out.cpu().numpy()
+    for c in range(2):
+        truth = onp.stft_f64(xs[c], n_fft, hop)
+        assert np.all(rel_l2(S[c].astype(np.complex128), truth, axis=1) <= TOL)
+        assert rel_max(M[c], np.abs(truth) + 1e-7) <= TOL
+        _check_sinc(out[c], ref_pos, xs[c], nt)
+    assert L.par_kernel_launch_count() > 0
