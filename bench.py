@@ -252,14 +252,18 @@ def main():
     T = int(L.par_stft_num_frames(n, N_FFT, HOP))
     F = N_FFT // 2 + 1
 
-    # ---- inputs: host (pinned, interleaved like the reference's (frames, channels) arrays) + device planar
-    host_planar = _lib.pinned_empty((C, n), np.float32)
+    # ---- inputs: host (pinned, interleaved (frames, channels) like the arrays soundfile hands the
+    #      reference, util/io_ops.py:10) + device planar copy for the device-resident arm
+    host_sig = _lib.pinned_empty((n, C), np.float32)
+    tmp_ch = np.empty(n, np.float32)
     for i, c in enumerate(my_ch):
-        synth_channel(n, sr, 1234 + c, out=host_planar[i])
+        synth_channel(n, sr, 1234 + c, out=tmp_ch)
+        host_sig[:, i] = tmp_ch
+    del tmp_ch
     curve = wow_curve(dur, sr)
     curve_t = torch.from_numpy(curve.copy()).to(dev)
     window = np.ascontiguousarray(__import__("scipy.signal").signal.get_window("blackmanharris", N_FFT), dtype=np.float32)
-    x_dev = torch.from_numpy(host_planar).to(dev)
+    x_dev = torch.from_numpy(host_sig).to(dev).t().contiguous()
     S_dev = torch.empty((C, T, F), dtype=torch.complex64, device=dev)
     cap = int(n * 1.02) + 4096
     pos_dev = torch.empty(cap, dtype=torch.float64, device=dev)
@@ -350,14 +354,13 @@ def main():
     # ---- e2e through the reference-facing API (host buffers in, host arrays out)
     e2e = None
     if not args.no_e2e:
-        sig = host_planar.T                              # (frames, channels) view, like io_ops.read_file returns
+        sig = host_sig
         speed_curve = curve
 
         def e2e_step():
-            res = [fourier.stft(sig[:, c], N_FFT, HOP) for c in range(C)]
-            sample_at = resampling.speed_to_pos(speed_curve[:, 0] * sr, speed_curve[:, 1], n)
-            out = resampling.resample_channels(sig, sample_at, range(C), "Sinc", NT)
-            return res, sample_at, out
+            res = [fourier.stft(sig[:, c], N_FFT, HOP) for c in range(C)]        # as the GUIs call it, per channel
+            out = resampling.varispeed(sig, sr, speed_curve, range(C), "Sinc", NT)   # run() minus the WAV write
+            return res, out
         for _ in range(2):
             r = e2e_step()
         del r
@@ -365,8 +368,8 @@ def main():
         t0 = time.perf_counter()
         e_steps = max(2, min(args.steps, 5))
         for _ in range(e_steps):
-            res, sample_at, out = e2e_step()
-            m_e = len(sample_at)
+            res, out = e2e_step()
+            m_e = out.shape[0]
             del res, out
         torch.cuda.synchronize(dev)
         dt = time.perf_counter() - t0
@@ -375,10 +378,12 @@ def main():
             dist.all_reduce(td, op=dist.ReduceOp.MAX)
             dt = float(td.item())
         e2e = {"value": samples_per_step * e_steps / dt, "unit": UNIT,
-               "h2d_bytes_per_step": int(C * n * 4 * 2 + m_e * 8 + len(curve) * 16 + N_FFT * 4),
-               "d2h_bytes_per_step": int(C * T * F * 8 + m_e * 8 + C * m_e * 4),
+               # stft(sig[:, c]) uploads the interleaved span of the column view (C*n floats) per call
+               "h2d_bytes_per_step": int(C * (C * n * 4) + C * n * 4 + len(curve) * 40 + N_FFT * 4),
+               "d2h_bytes_per_step": int(C * T * F * 8 + C * m_e * 4 + len(curve) * 8),
                "steps": e_steps, "ms_per_step": dt / e_steps * 1e3,
-               "api": "util.fourier.stft per channel + util.resampling.speed_to_pos + resample_channels (body of run())"}
+               "api": "util.fourier.stft(sig[:, c]) per channel + util.resampling.varispeed (= run() minus the WAV write), "
+                      "interleaved pinned float32 (frames, channels) in, pinned numpy arrays out"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

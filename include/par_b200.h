@@ -131,6 +131,18 @@ PAR_API int par_linear_resample_f32(const double *pos, int64_t m, const float *s
                             float *out, int64_t out_stride, int64_t out_ch_stride,
                             unsigned flags, int device, void *stream);
 
+/* ---- speed curve -> resampled audio in one call: the "Preparing" + "Resampling" phases of
+ *      util/resampling.py:162-231 (run) with speed_curve given.  Positions are expanded on the
+ *      device and never leave it.  out holds out_cap samples per channel; *m receives the number
+ *      of samples written per channel (PAR_ECAPACITY, with *m set, if out_cap is too small;
+ *      sum(par_speed_segments) always suffices).  mode: PAR_MODE_LINEAR | PAR_MODE_SINC. */
+#define PAR_MODE_LINEAR 0
+#define PAR_MODE_SINC 1
+PAR_API int par_varispeed_f32(const double *sampletimes, const double *speeds, int64_t k,
+                      const float *signal, int64_t n_in, int64_t sig_stride, int n_ch, int64_t sig_ch_stride,
+                      int mode, int nt, float *out, int64_t out_cap, int64_t out_stride, int64_t out_ch_stride,
+                      int64_t *m, unsigned flags, int device, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,12 +17,14 @@ PAR_DEVICE_PTRS = 1 << 0
 PAR_OUT_MAGNITUDE = 1 << 1
 PAR_SINC_ALIGNED_EDGES = 1 << 2
 PAR_ECAPACITY = -4
+PAR_MODE_LINEAR = 0
+PAR_MODE_SINC = 1
 
 EXPORTS = (
     "par_last_error", "par_version", "par_device_count", "par_kernel_launch_count",
     "par_last_kernel_ms", "par_host_alloc", "par_host_free", "par_stft_num_frames", "par_stft_f32",
     "par_istft_f32", "par_speed_segments", "par_speed_to_pos_f64", "par_sinc_resample_f32",
-    "par_linear_resample_f32",
+    "par_linear_resample_f32", "par_varispeed_f32",
 )
 
 
@@ -63,6 +65,9 @@ def _declare(L):
     L.par_sinc_resample_f32.argtypes = [vp, i64, vp, i64, i64, i32, i64, i32, vp, i64, i64, u32, i32, vp]
     L.par_linear_resample_f32.restype = i32
     L.par_linear_resample_f32.argtypes = [vp, i64, vp, i64, i64, i32, i64, vp, i64, i64, u32, i32, vp]
+    L.par_varispeed_f32.restype = i32
+    L.par_varispeed_f32.argtypes = [vp, vp, i64, vp, i64, i64, i32, i64, i32, i32, vp, i64, i64, i64, vp, u32,
+                                    i32, vp]
 
 
 def lib():
@@ -151,3 +156,32 @@ def pinned_empty(shape, dtype):
     shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
     dtype = np.dtype(dtype)
     return _Pinned(int(np.prod(shape)) * dtype.itemsize).array(shape, dtype)
+
+
+def f32_layout(a):
+    """(array to keep alive, data pointer, element stride) of a 1-D real array for the C ABI:
+    float32 views with a positive element stride are passed as they lie in memory (no host copy --
+    the library uploads the interleaved span and reads it strided); anything else is converted."""
+    a = np.asarray(a)
+    if a.ndim != 1:
+        raise ValueError("expected a 1-D array")
+    ok = a.dtype == np.float32 and (len(a) <= 1 or (a.strides[0] > 0 and a.strides[0] % 4 == 0))
+    if not ok:
+        a = np.ascontiguousarray(a, dtype=np.float32)
+    stride = a.strides[0] // 4 if len(a) > 1 else 1
+    return a, a.ctypes.data, max(int(stride), 1)
+
+
+def f32_layout_2d(a):
+    """(array, pointer, frame stride, channel stride) of a (frames, channels) float32 array, in
+    elements; copies only when the strides are not positive multiples of 4 bytes."""
+    a = np.asarray(a)
+    if a.ndim != 2:
+        raise ValueError("expected a (frames, channels) array")
+    def good(st, n):
+        return n <= 1 or (st > 0 and st % 4 == 0)
+    if a.dtype != np.float32 or not good(a.strides[0], a.shape[0]) or not good(a.strides[1], a.shape[1]):
+        a = np.ascontiguousarray(a, dtype=np.float32)
+    fs = a.strides[0] // 4 if a.shape[0] > 1 else max(a.shape[1], 1)
+    cs = a.strides[1] // 4 if a.shape[1] > 1 else 1
+    return a, a.ctypes.data, max(int(fs), 1), max(int(cs), 0)

@@ -197,29 +197,87 @@ struct EventTimer {
 	~EventTimer() { cudaEventDestroy(a); cudaEventDestroy(b); }
 };
 
-// strided host channel <-> planar device copies
-static int h2d_channels(float *dst, int64_t dst_ch_stride, const float *src, int64_t n, int64_t stride,
-                        int n_ch, int64_t ch_stride, cudaStream_t st) {
+// ---- host <-> device staging of audio ---------------------------------------------------------
+// A host channel set (n samples, element stride `stride`, channel c at +c*ch_stride) is uploaded
+//  (a) planar, one contiguous copy per channel, when stride == 1;
+//  (b) as ONE contiguous copy of the whole interleaved span when the channels interleave inside
+//      the sample stride (the reference's (frames, channels) arrays and column views of them) and the
+//      span is at most 4x the useful bytes -- the kernels then read it with the host's strides;
+//  (c) with a strided 2-D copy per channel otherwise (slow, correct).
+struct DevAudio {
+	float *p = nullptr;
+	int64_t stride = 1, ch_stride = 0;
+};
+
+static int upload_audio(DevBuf &buf, const float *src, int64_t n, int64_t stride, int n_ch, int64_t ch_stride,
+                        cudaStream_t st, DevAudio *out) {
+	int rc;
+	const int64_t n_al = ((n > 0 ? n : 1) + 3) & ~(int64_t)3;
+	const int64_t span = (n - 1) * stride + (int64_t)(n_ch - 1) * ch_stride + 1;
+	const bool interleaved = stride > 1 && (n_ch == 1 || (ch_stride > 0 && ch_stride < stride)) &&
+	                         span <= 4 * n * (int64_t)n_ch + 64;
+	if (n <= 0) {
+		if ((rc = buf.alloc(16)) != PAR_OK) return rc;
+		out->p = buf.as<float>(); out->stride = 1; out->ch_stride = 0;
+		return PAR_OK;
+	}
+	if (interleaved) {
+		if ((rc = buf.alloc((size_t)(span + 4) * sizeof(float))) != PAR_OK) return rc;
+		PAR_CUDA(cudaMemcpyAsync(buf.p, src, (size_t)span * sizeof(float), cudaMemcpyHostToDevice, st));
+		out->p = buf.as<float>(); out->stride = stride; out->ch_stride = ch_stride;
+		return PAR_OK;
+	}
+	if ((rc = buf.alloc((size_t)n_al * n_ch * sizeof(float))) != PAR_OK) return rc;
 	for (int c = 0; c < n_ch; c++) {
+		float *dst = buf.as<float>() + c * n_al;
 		if (stride == 1) {
-			PAR_CUDA(cudaMemcpyAsync(dst + c * dst_ch_stride, src + c * ch_stride, n * sizeof(float),
-			                         cudaMemcpyHostToDevice, st));
+			PAR_CUDA(cudaMemcpyAsync(dst, src + c * ch_stride, n * sizeof(float), cudaMemcpyHostToDevice, st));
 		} else {
-			PAR_CUDA(cudaMemcpy2DAsync(dst + c * dst_ch_stride, sizeof(float), src + c * ch_stride,
-			                           stride * sizeof(float), sizeof(float), n, cudaMemcpyHostToDevice, st));
+			PAR_CUDA(cudaMemcpy2DAsync(dst, sizeof(float), src + c * ch_stride, stride * sizeof(float),
+			                           sizeof(float), n, cudaMemcpyHostToDevice, st));
 		}
 	}
+	out->p = buf.as<float>(); out->stride = 1; out->ch_stride = n_al;
 	return PAR_OK;
 }
-static int d2h_channels(float *dst, int64_t n, int64_t stride, int n_ch, int64_t ch_stride, const float *src,
-                        int64_t src_ch_stride, cudaStream_t st) {
+
+// Device-side image of a host output channel set.  When the channels tile the host span exactly
+// (fully interleaved: ch_stride 1, stride n_ch; or one contiguous channel) the kernel writes the
+// host layout and ONE contiguous copy brings it back; otherwise planar + per-channel copies.
+struct DevOut {
+	float *p = nullptr;
+	int64_t stride = 1, ch_stride = 0;
+	bool image = false;
+};
+
+static int alloc_out(DevBuf &buf, int64_t m, int64_t stride, int n_ch, int64_t ch_stride, cudaStream_t st, DevOut *o) {
+	(void)st;
+	int rc;
+	const int64_t mm = m > 0 ? m : 1;
+	if (n_ch > 1 && ch_stride == 1 && stride == n_ch) {
+		if ((rc = buf.alloc((size_t)mm * n_ch * sizeof(float))) != PAR_OK) return rc;
+		o->p = buf.as<float>(); o->stride = stride; o->ch_stride = 1; o->image = true;
+		return PAR_OK;
+	}
+	if ((rc = buf.alloc((size_t)mm * n_ch * sizeof(float))) != PAR_OK) return rc;
+	o->p = buf.as<float>(); o->stride = 1; o->ch_stride = mm; o->image = false;
+	return PAR_OK;
+}
+
+static int download_out(const DevOut &o, float *dst, int64_t m, int64_t stride, int n_ch, int64_t ch_stride,
+                        cudaStream_t st) {
+	if (m <= 0) return PAR_OK;
+	if (o.image) {
+		PAR_CUDA(cudaMemcpyAsync(dst, o.p, (size_t)m * n_ch * sizeof(float), cudaMemcpyDeviceToHost, st));
+		return PAR_OK;
+	}
 	for (int c = 0; c < n_ch; c++) {
 		if (stride == 1) {
-			PAR_CUDA(cudaMemcpyAsync(dst + c * ch_stride, src + c * src_ch_stride, n * sizeof(float),
+			PAR_CUDA(cudaMemcpyAsync(dst + c * ch_stride, o.p + c * o.ch_stride, m * sizeof(float),
 			                         cudaMemcpyDeviceToHost, st));
 		} else {
-			PAR_CUDA(cudaMemcpy2DAsync(dst + c * ch_stride, stride * sizeof(float), src + c * src_ch_stride,
-			                           sizeof(float), sizeof(float), n, cudaMemcpyDeviceToHost, st));
+			PAR_CUDA(cudaMemcpy2DAsync(dst + c * ch_stride, stride * sizeof(float), o.p + c * o.ch_stride,
+			                           sizeof(float), sizeof(float), m, cudaMemcpyDeviceToHost, st));
 		}
 	}
 	return PAR_OK;
@@ -283,17 +341,25 @@ PAR_API int par_stft_f32(const float *x, int64_t n, int64_t x_stride, int n_ch, 
 		a.out = out; a.out_pitch = out_pitch; a.out_ch_stride = out_ch_stride;
 		return launch_stft(a, device, st);
 	}
-	// host pointers: stage planar input, run, copy the rows back
+	// host pointers: upload (in the host's own layout), de-interleave on the device if needed, run,
+	// copy the rows back
 	const size_t esz = mag ? sizeof(float) : sizeof(float2);
 	const int64_t n_al = (n + 3) & ~(int64_t)3;
-	DevBuf dx(st), dout(st);
-	if ((rc = dx.alloc((size_t)n_al * n_ch * sizeof(float))) != PAR_OK) return rc;
+	DevBuf dx(st), dplanar(st), dout(st);
+	DevAudio da;
+	if ((rc = upload_audio(dx, x, n, x_stride, n_ch, x_ch_stride, st, &da)) != PAR_OK) return rc;
 	if ((rc = dout.alloc((size_t)T * F * n_ch * esz)) != PAR_OK) return rc;
-	if ((rc = h2d_channels(dx.as<float>(), n_al, x, n, x_stride, n_ch, x_ch_stride, st)) != PAR_OK) return rc;
-	a.x = dx.as<float>(); a.x_stride = 1; a.x_ch_stride = n_al;
-	a.out = dout.p; a.out_pitch = F; a.out_ch_stride = T * F;
 	EventTimer tm(st);
 	tm.start();
+	if (da.stride != 1) {
+		if ((rc = dplanar.alloc((size_t)n_al * n_ch * sizeof(float))) != PAR_OK) return rc;
+		if ((rc = launch_deinterleave(da.p, n, da.stride, n_ch, da.ch_stride, dplanar.as<float>(), n_al, device, st)) != PAR_OK)
+			return rc;
+		a.x = dplanar.as<float>(); a.x_stride = 1; a.x_ch_stride = n_al;
+	} else {
+		a.x = da.p; a.x_stride = 1; a.x_ch_stride = da.ch_stride;
+	}
+	a.out = dout.p; a.out_pitch = F; a.out_ch_stride = T * F;
 	if ((rc = launch_stft(a, device, st)) != PAR_OK) return rc;
 	tm.stop();
 	for (int c = 0; c < n_ch; c++) {
@@ -337,8 +403,9 @@ PAR_API int par_istft_f32(const void *S, int n_fft, int64_t n_frames, int64_t s_
 		return launch_istft(a, device, st);
 	}
 	DevBuf ds(st), dy(st);
+	DevOut dyo;
 	if ((rc = ds.alloc((size_t)n_ch * n_frames * F * sizeof(float2))) != PAR_OK) return rc;
-	if ((rc = dy.alloc((size_t)n_ch * (length > 0 ? length : 1) * sizeof(float))) != PAR_OK) return rc;
+	if ((rc = alloc_out(dy, length, y_stride, n_ch, y_ch_stride, st, &dyo)) != PAR_OK) return rc;
 	for (int c = 0; c < n_ch; c++) {
 		const char *src = (const char *)S + (size_t)c * s_ch_stride * sizeof(float2);
 		char *dst = (char *)ds.p + (size_t)c * n_frames * F * sizeof(float2);
@@ -346,13 +413,12 @@ PAR_API int par_istft_f32(const void *S, int n_fft, int64_t n_frames, int64_t s_
 		                           n_frames, cudaMemcpyHostToDevice, st));
 	}
 	a.S = ds.as<float2>(); a.s_pitch = F; a.s_ch_stride = n_frames * F;
-	a.y = dy.as<float>(); a.y_stride = 1; a.y_ch_stride = length;
+	a.y = dyo.p; a.y_stride = dyo.stride; a.y_ch_stride = dyo.ch_stride;
 	EventTimer tm(st);
 	tm.start();
 	if ((rc = launch_istft(a, device, st)) != PAR_OK) return rc;
 	tm.stop();
-	if (length > 0 && (rc = d2h_channels(y, length, y_stride, n_ch, y_ch_stride, dy.as<float>(), length, st)) != PAR_OK)
-		return rc;
+	if ((rc = download_out(dyo, y, length, y_stride, n_ch, y_ch_stride, st)) != PAR_OK) return rc;
 	PAR_CUDA(cudaStreamSynchronize(st));
 	tm.finish();
 	return PAR_OK;
@@ -380,20 +446,15 @@ PAR_API int par_speed_segments(const double *sampletimes, const double *speeds, 
 	return PAR_OK;
 }
 
-PAR_API int par_speed_to_pos_f64(const double *sampletimes, const double *speeds, int64_t k,
-                         double num_input_samples, double *pos, int64_t cap, int64_t *m,
-                         unsigned flags, int device, void *stream) {
-	if (!sampletimes || !speeds || k < 2 || !m || (!pos && cap > 0)) {
-		set_error("speed_to_pos: bad argument");
-		return PAR_EINVAL;
-	}
-	int rc = use_device(device);
-	if (rc != PAR_OK) return rc;
-	cudaStream_t st = (cudaStream_t)stream;
+// Speed curve -> device-resident read positions.  `pos` must hold `cap` doubles on the device;
+// *m_out receives the number of valid positions.  Synchronises `st` once (the per-segment sums
+// have to reach the host for the serial offset chain and the end test, util/resampling.py:125-135).
+static int positions_device(const double *sampletimes, const double *speeds, int64_t k, double num_input_samples,
+                            const std::vector<int64_t> &seg_n, int64_t total, double *pos, int64_t cap,
+                            int64_t *m_out, cudaStream_t st) {
+	int rc;
 	const int64_t n_seg = k - 1;
-	std::vector<int64_t> seg_n(n_seg), seg_start(n_seg);
-	int64_t total = 0;
-	if ((rc = par_speed_segments(sampletimes, speeds, k, seg_n.data(), &total)) != PAR_OK) return rc;
+	std::vector<int64_t> seg_start(n_seg);
 	int64_t o = 0;
 	for (int64_t i = 0; i < n_seg; i++) { seg_start[i] = o; if (seg_n[i] > 0) o += seg_n[i]; }
 
@@ -405,6 +466,7 @@ PAR_API int par_speed_to_pos_f64(const double *sampletimes, const double *speeds
 	if ((rc = d_off.alloc(n_seg * sizeof(double))) != PAR_OK) return rc;
 	PAR_CUDA(cudaMemcpyAsync(d_sp.p, speeds, k * sizeof(double), cudaMemcpyHostToDevice, st));
 	PAR_CUDA(cudaMemcpyAsync(d_n.p, seg_n.data(), n_seg * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+	PAR_CUDA(cudaMemcpyAsync(d_start.p, seg_start.data(), n_seg * sizeof(int64_t), cudaMemcpyHostToDevice, st));
 	if ((rc = launch_segment_sums(d_sp.as<double>(), d_n.as<int64_t>(), n_seg, d_sum.as<double>(), st)) != PAR_OK)
 		return rc;
 	std::vector<double> sums(n_seg), off(n_seg);
@@ -413,7 +475,7 @@ PAR_API int par_speed_to_pos_f64(const double *sampletimes, const double *speeds
 
 	// serial offset chain + end test (util/resampling.py:125-135)
 	volatile double offset = sampletimes[0];
-	int64_t m_out = total;
+	int64_t m = total;
 	for (int64_t i = 0; i < n_seg; i++) {
 		off[i] = offset;
 		const int64_t n = seg_n[i];
@@ -435,37 +497,96 @@ PAR_API int par_speed_to_pos_f64(const double *sampletimes, const double *speeds
 				v = v + speeds[i];
 				volatile double r = 1.0 / v;
 				acc = acc + r;
-				volatile double p = acc + offset;
-				const double dist = fabs(p - num_input_samples);
+				volatile double pj = acc + offset;
+				const double dist = fabs(pj - num_input_samples);
 				if (dist < best) { best = dist; besti = j; }
 			}
-			m_out = seg_start[i] + besti;
+			m = seg_start[i] + besti;
 			break;
 		}
 		offset = last;
 	}
-	*m = m_out;
-	if (m_out > cap) {
+	*m_out = m;
+	if (m > cap) {
 		set_error("speed_to_pos: output capacity too small");
 		return PAR_ECAPACITY;
 	}
-	if (m_out == 0) return PAR_OK;
-	PAR_CUDA(cudaMemcpyAsync(d_start.p, seg_start.data(), n_seg * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+	if (m == 0) return PAR_OK;
 	PAR_CUDA(cudaMemcpyAsync(d_off.p, off.data(), n_seg * sizeof(double), cudaMemcpyHostToDevice, st));
-	if (flags & PAR_DEVICE_PTRS) {
-		rc = launch_expand_positions(d_sp.as<double>(), d_n.as<int64_t>(), d_start.as<int64_t>(), d_off.as<double>(),
-		                             n_seg, pos, m_out, st);
-		if (rc != PAR_OK) return rc;
-		PAR_CUDA(cudaStreamSynchronize(st));  // host vectors above must outlive the async copies
-		return PAR_OK;
-	}
-	DevBuf d_pos(st);
-	if ((rc = d_pos.alloc(m_out * sizeof(double))) != PAR_OK) return rc;
 	rc = launch_expand_positions(d_sp.as<double>(), d_n.as<int64_t>(), d_start.as<int64_t>(), d_off.as<double>(),
-	                             n_seg, d_pos.as<double>(), m_out, st);
+	                             n_seg, pos, m, st);
 	if (rc != PAR_OK) return rc;
-	PAR_CUDA(cudaMemcpyAsync(pos, d_pos.p, m_out * sizeof(double), cudaMemcpyDeviceToHost, st));
+	// `off` (pageable) must outlive its async copy
 	PAR_CUDA(cudaStreamSynchronize(st));
+	return PAR_OK;
+}
+
+PAR_API int par_speed_to_pos_f64(const double *sampletimes, const double *speeds, int64_t k,
+                         double num_input_samples, double *pos, int64_t cap, int64_t *m,
+                         unsigned flags, int device, void *stream) {
+	if (!sampletimes || !speeds || k < 2 || !m || (!pos && cap > 0)) {
+		set_error("speed_to_pos: bad argument");
+		return PAR_EINVAL;
+	}
+	int rc = use_device(device);
+	if (rc != PAR_OK) return rc;
+	cudaStream_t st = (cudaStream_t)stream;
+	std::vector<int64_t> seg_n(k - 1);
+	int64_t total = 0;
+	if ((rc = par_speed_segments(sampletimes, speeds, k, seg_n.data(), &total)) != PAR_OK) return rc;
+	if (flags & PAR_DEVICE_PTRS)
+		return positions_device(sampletimes, speeds, k, num_input_samples, seg_n, total, pos, cap, m, st);
+	DevBuf d_pos(st);
+	const int64_t dcap = total < cap ? total : cap;
+	if ((rc = d_pos.alloc((size_t)(dcap > 0 ? dcap : 1) * sizeof(double))) != PAR_OK) return rc;
+	rc = positions_device(sampletimes, speeds, k, num_input_samples, seg_n, total, d_pos.as<double>(), dcap, m, st);
+	if (rc != PAR_OK) return rc;
+	if (*m > 0) {
+		PAR_CUDA(cudaMemcpyAsync(pos, d_pos.p, *m * sizeof(double), cudaMemcpyDeviceToHost, st));
+		PAR_CUDA(cudaStreamSynchronize(st));
+	}
+	return PAR_OK;
+}
+
+// Resample with DEVICE positions; signal / out are host or device according to `flags`.
+static int resample_with_dev_pos(bool sinc, const double *dpos, int64_t m, const float *signal, int64_t n_in,
+                                 int64_t sig_stride, int n_ch, int64_t sig_ch_stride, int nt,
+                                 float *out, int64_t out_stride, int64_t out_ch_stride,
+                                 unsigned flags, int device, cudaStream_t st) {
+	int rc;
+	SincArgs a;
+	a.pos = dpos; a.m = m; a.n_in = n_in; a.n_ch = n_ch; a.nt = nt;
+	a.aligned_edges = (flags & PAR_SINC_ALIGNED_EDGES) ? 1 : 0;
+	if (flags & PAR_DEVICE_PTRS) {
+		a.signal = signal; a.sig_stride = sig_stride; a.sig_ch_stride = sig_ch_stride;
+		a.out = out; a.out_stride = out_stride; a.out_ch_stride = out_ch_stride;
+		return sinc ? launch_sinc(a, device, st) : launch_linear(a, device, st);
+	}
+	DevBuf dsig(st), dout(st);
+	DevAudio da;
+	DevOut dd;
+	if ((rc = upload_audio(dsig, signal, n_in, sig_stride, n_ch, sig_ch_stride, st, &da)) != PAR_OK) return rc;
+	if ((rc = alloc_out(dout, m, out_stride, n_ch, out_ch_stride, st, &dd)) != PAR_OK) return rc;
+	a.signal = da.p; a.sig_stride = da.stride; a.sig_ch_stride = da.ch_stride;
+	a.out = dd.p; a.out_stride = dd.stride; a.out_ch_stride = dd.ch_stride;
+	EventTimer tm(st);
+	tm.start();
+	if ((rc = sinc ? launch_sinc(a, device, st) : launch_linear(a, device, st)) != PAR_OK) return rc;
+	tm.stop();
+	if ((rc = download_out(dd, out, m, out_stride, n_ch, out_ch_stride, st)) != PAR_OK) return rc;
+	PAR_CUDA(cudaStreamSynchronize(st));
+	tm.finish();
+	return PAR_OK;
+}
+
+static int check_resample_args(bool sinc, int64_t m, const void *pos_or_curve, const float *signal, int64_t n_in,
+                               int64_t sig_stride, int n_ch, int nt, const float *out, int64_t out_stride) {
+	if (m < 0 || n_in < 0 || n_ch < 1 || sig_stride < 1 || out_stride < 1 || (sinc && (nt < 1 || nt > 512))) {
+		set_error("resample: bad size argument");
+		return PAR_EINVAL;
+	}
+	if (m > 0 && (!pos_or_curve || !out)) { set_error("resample: null pointer"); return PAR_EINVAL; }
+	if (n_in > 0 && !signal) { set_error("resample: null signal"); return PAR_EINVAL; }
 	return PAR_OK;
 }
 
@@ -473,43 +594,19 @@ static int resample_common(bool sinc, const double *pos, int64_t m, const float 
                            int64_t sig_stride, int n_ch, int64_t sig_ch_stride, int nt,
                            float *out, int64_t out_stride, int64_t out_ch_stride,
                            unsigned flags, int device, void *stream) {
-	if (m < 0 || n_in < 0 || n_ch < 1 || sig_stride < 1 || out_stride < 1 || (sinc && (nt < 1 || nt > 512))) {
-		set_error("resample: bad size argument");
-		return PAR_EINVAL;
-	}
-	if (m > 0 && (!pos || !out)) { set_error("resample: null pointer"); return PAR_EINVAL; }
-	if (n_in > 0 && !signal) { set_error("resample: null signal"); return PAR_EINVAL; }
-	int rc = use_device(device);
+	int rc = check_resample_args(sinc, m, pos, signal, n_in, sig_stride, n_ch, nt, out, out_stride);
 	if (rc != PAR_OK) return rc;
+	if ((rc = use_device(device)) != PAR_OK) return rc;
 	if (m == 0) return PAR_OK;
 	cudaStream_t st = (cudaStream_t)stream;
-	SincArgs a;
-	a.m = m; a.n_in = n_in; a.n_ch = n_ch; a.nt = nt;
-	a.aligned_edges = (flags & PAR_SINC_ALIGNED_EDGES) ? 1 : 0;
-	if (flags & PAR_DEVICE_PTRS) {
-		a.pos = pos; a.signal = signal; a.sig_stride = sig_stride; a.sig_ch_stride = sig_ch_stride;
-		a.out = out; a.out_stride = out_stride; a.out_ch_stride = out_ch_stride;
-		return sinc ? launch_sinc(a, device, st) : launch_linear(a, device, st);
-	}
-	const int64_t n_al = ((n_in > 0 ? n_in : 1) + 3) & ~(int64_t)3;
-	DevBuf dpos(st), dsig(st), dout(st);
+	if (flags & PAR_DEVICE_PTRS)
+		return resample_with_dev_pos(sinc, pos, m, signal, n_in, sig_stride, n_ch, sig_ch_stride, nt, out, out_stride,
+		                             out_ch_stride, flags, device, st);
+	DevBuf dpos(st);
 	if ((rc = dpos.alloc(m * sizeof(double))) != PAR_OK) return rc;
-	if ((rc = dsig.alloc((size_t)n_al * n_ch * sizeof(float))) != PAR_OK) return rc;
-	if ((rc = dout.alloc((size_t)m * n_ch * sizeof(float))) != PAR_OK) return rc;
 	PAR_CUDA(cudaMemcpyAsync(dpos.p, pos, m * sizeof(double), cudaMemcpyHostToDevice, st));
-	if (n_in > 0 &&
-	    (rc = h2d_channels(dsig.as<float>(), n_al, signal, n_in, sig_stride, n_ch, sig_ch_stride, st)) != PAR_OK)
-		return rc;
-	a.pos = dpos.as<double>(); a.signal = dsig.as<float>(); a.sig_stride = 1; a.sig_ch_stride = n_al;
-	a.out = dout.as<float>(); a.out_stride = 1; a.out_ch_stride = m;
-	EventTimer tm(st);
-	tm.start();
-	if ((rc = sinc ? launch_sinc(a, device, st) : launch_linear(a, device, st)) != PAR_OK) return rc;
-	tm.stop();
-	if ((rc = d2h_channels(out, m, out_stride, n_ch, out_ch_stride, dout.as<float>(), m, st)) != PAR_OK) return rc;
-	PAR_CUDA(cudaStreamSynchronize(st));
-	tm.finish();
-	return PAR_OK;
+	return resample_with_dev_pos(sinc, dpos.as<double>(), m, signal, n_in, sig_stride, n_ch, sig_ch_stride, nt, out,
+	                             out_stride, out_ch_stride, flags, device, st);
 }
 
 PAR_API int par_sinc_resample_f32(const double *pos, int64_t m, const float *signal, int64_t n_in,
@@ -526,6 +623,35 @@ PAR_API int par_linear_resample_f32(const double *pos, int64_t m, const float *s
                             unsigned flags, int device, void *stream) {
 	return resample_common(false, pos, m, signal, n_in, sig_stride, n_ch, sig_ch_stride, 1, out, out_stride,
 	                       out_ch_stride, flags, device, stream);
+}
+
+PAR_API int par_varispeed_f32(const double *sampletimes, const double *speeds, int64_t k,
+                      const float *signal, int64_t n_in, int64_t sig_stride, int n_ch, int64_t sig_ch_stride,
+                      int mode, int nt, float *out, int64_t out_cap, int64_t out_stride, int64_t out_ch_stride,
+                      int64_t *m, unsigned flags, int device, void *stream) {
+	if (!sampletimes || !speeds || k < 2 || !m || (mode != PAR_MODE_LINEAR && mode != PAR_MODE_SINC)) {
+		set_error("varispeed: bad argument");
+		return PAR_EINVAL;
+	}
+	const bool sinc = mode == PAR_MODE_SINC;
+	int rc = check_resample_args(sinc, out_cap, sampletimes, signal, n_in, sig_stride, n_ch, nt, out, out_stride);
+	if (rc != PAR_OK) return rc;
+	if ((rc = use_device(device)) != PAR_OK) return rc;
+	cudaStream_t st = (cudaStream_t)stream;
+	std::vector<int64_t> seg_n(k - 1);
+	int64_t total = 0;
+	if ((rc = par_speed_segments(sampletimes, speeds, k, seg_n.data(), &total)) != PAR_OK) return rc;
+	DevBuf dpos(st);
+	if ((rc = dpos.alloc((size_t)(total > 0 ? total : 1) * sizeof(double))) != PAR_OK) return rc;
+	rc = positions_device(sampletimes, speeds, k, (double)n_in, seg_n, total, dpos.as<double>(), total, m, st);
+	if (rc != PAR_OK) return rc;
+	if (*m > out_cap) {
+		set_error("varispeed: output capacity too small (need *m samples per channel)");
+		return PAR_ECAPACITY;
+	}
+	if (*m == 0) return PAR_OK;
+	return resample_with_dev_pos(sinc, dpos.as<double>(), *m, signal, n_in, sig_stride, n_ch, sig_ch_stride, nt, out,
+	                             out_stride, out_ch_stride, flags, device, st);
 }
 
 }  // extern "C"

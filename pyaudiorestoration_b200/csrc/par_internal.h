@@ -74,5 +74,8 @@ struct SincArgs {
 };
 int launch_sinc(const SincArgs &a, int device, cudaStream_t st);
 int launch_linear(const SincArgs &a, int device, cudaStream_t st);
+// dst[c * dst_ch_stride + i] = src[i * stride + c * ch_stride]
+int launch_deinterleave(const float *src, int64_t n, int64_t stride, int n_ch, int64_t ch_stride, float *dst,
+                        int64_t dst_ch_stride, int device, cudaStream_t st);
 
 }  // namespace par

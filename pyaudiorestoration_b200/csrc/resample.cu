@@ -41,28 +41,63 @@ segment_sums_kernel(const double *__restrict__ speeds, const int64_t *__restrict
 	const double ds = __dsub_rn(speeds[i + 1], s0);
 	const double nm1 = (double)(n - 1);
 	double acc = 0.0;
-	for (int64_t j = 0; j < n; j++) acc = __dadd_rn(acc, __ddiv_rn(1.0, seg_speed(j, nm1, ds, s0)));
+	int64_t j = 0;
+	for (; j + 8 <= n; j += 8) {      // the divisions are independent: let them pipeline
+		double r[8];
+#pragma unroll
+		for (int u = 0; u < 8; u++) r[u] = __ddiv_rn(1.0, seg_speed(j + u, nm1, ds, s0));
+#pragma unroll
+		for (int u = 0; u < 8; u++) acc = __dadd_rn(acc, r[u]);
+	}
+	for (; j < n; j++) acc = __dadd_rn(acc, __ddiv_rn(1.0, seg_speed(j, nm1, ds, s0)));
 	sums[i] = acc;
 }
 
-__global__ void __launch_bounds__(128)
+// One thread per segment (the cumsum is serial in float64 by contract), but the stores go through
+// a per-warp shared-memory tile so that every segment's 32-position run leaves as one 256-byte
+// coalesced write instead of 32 scattered 8-byte ones.
+constexpr int EXP_WARPS = 4;
+__global__ void __launch_bounds__(32 * EXP_WARPS)
 expand_positions_kernel(const double *__restrict__ speeds, const int64_t *__restrict__ seg_n,
                         const int64_t *__restrict__ seg_start, const double *__restrict__ seg_off,
                         int64_t n_seg, double *__restrict__ pos, int64_t m) {
+	__shared__ double tile[EXP_WARPS][32][33];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-	if (i >= n_seg) return;
-	const int64_t start = seg_start[i];
-	int64_t n = seg_n[i];
-	if (start >= m || n <= 0) return;
-	const double s0 = speeds[i];
-	const double ds = __dsub_rn(speeds[i + 1], s0);
-	const double nm1 = (double)(n - 1);
-	const double off = seg_off[i];
-	if (start + n > m) n = m - start;
+	int64_t start = 0, n = 0;
+	double s0 = 1.0, ds = 0.0, nm1 = 1.0, off = 0.0;
+	if (i < n_seg) {
+		start = seg_start[i];
+		n = seg_n[i];
+		if (n < 0 || start >= m) n = 0;
+		if (start + n > m) n = m - start;
+		s0 = speeds[i];
+		ds = __dsub_rn(speeds[i + 1], s0);
+		nm1 = (double)(seg_n[i] - 1);
+		off = seg_off[i];
+	}
+	int64_t nmax = n;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
 	double acc = 0.0;
-	for (int64_t j = 0; j < n; j++) {
-		acc = __dadd_rn(acc, __ddiv_rn(1.0, seg_speed(j, nm1, ds, s0)));
-		pos[start + j] = __dadd_rn(acc, off);
+	for (int64_t j0 = 0; j0 < nmax; j0 += 32) {
+		if (j0 < n) {
+			double r[32];
+#pragma unroll
+			for (int jj = 0; jj < 32; jj++) r[jj] = __ddiv_rn(1.0, seg_speed(j0 + jj, nm1, ds, s0));
+#pragma unroll
+			for (int jj = 0; jj < 32; jj++) {
+				acc = __dadd_rn(acc, r[jj]);
+				tile[warp][lane][jj] = __dadd_rn(acc, off);
+			}
+		}
+		__syncwarp();
+		for (int row = 0; row < 32; row++) {
+			const int64_t rn = __shfl_sync(0xffffffffu, n, row);
+			const int64_t rs = __shfl_sync(0xffffffffu, start, row);
+			if (j0 + lane < rn) pos[rs + j0 + lane] = tile[warp][row][lane];
+		}
+		__syncwarp();
 	}
 }
 
@@ -80,7 +115,8 @@ int launch_expand_positions(const double *speeds_dev, const int64_t *seg_n_dev,
                             const int64_t *seg_start_dev, const double *seg_offset_dev,
                             int64_t n_seg, double *pos_dev, int64_t m, cudaStream_t st) {
 	if (n_seg <= 0 || m <= 0) return PAR_OK;
-	expand_positions_kernel<<<(unsigned)((n_seg + 127) / 128), 128, 0, st>>>(
+	const int tpb = 32 * EXP_WARPS;
+	expand_positions_kernel<<<(unsigned)((n_seg + tpb - 1) / tpb), tpb, 0, st>>>(
 	    speeds_dev, seg_n_dev, seg_start_dev, seg_offset_dev, n_seg, pos_dev, m);
 	count_launch();
 	PAR_CUDA(cudaGetLastError());

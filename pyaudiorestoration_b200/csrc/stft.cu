@@ -48,6 +48,29 @@ struct FrameLoad {
 	}
 };
 
+// Planar copy of a strided channel set (host-pointer calls upload interleaved audio as it lies in
+// host memory; the transform kernel's vector loads want unit stride).
+__global__ void __launch_bounds__(256)
+deinterleave_kernel(const float *__restrict__ src, int64_t n, int64_t stride, int n_ch, int64_t ch_stride,
+                    float *__restrict__ dst, int64_t dst_ch_stride) {
+	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+		const float *s = src + i * stride;
+		for (int c = 0; c < n_ch; c++) dst[c * dst_ch_stride + i] = __ldg(s + c * ch_stride);
+	}
+}
+
+int launch_deinterleave(const float *src, int64_t n, int64_t stride, int n_ch, int64_t ch_stride, float *dst,
+                        int64_t dst_ch_stride, int device, cudaStream_t st) {
+	if (n <= 0 || n_ch <= 0) return PAR_OK;
+	int64_t grid = (n + 255) / 256;
+	const int64_t cap = (int64_t)sm_count(device) * 16;
+	if (grid > cap) grid = cap;
+	deinterleave_kernel<<<(unsigned)grid, 256, 0, st>>>(src, n, stride, n_ch, ch_stride, dst, dst_ch_stride);
+	count_launch();
+	PAR_CUDA(cudaGetLastError());
+	return PAR_OK;
+}
+
 template <int LOG2M>
 struct StftCfg {
 	using S = FftSched<LOG2M>;

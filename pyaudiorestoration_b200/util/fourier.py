@@ -35,22 +35,24 @@ def to_mag(spectrum):
     return abs(spectrum) + .0000001
 
 
-def _prep_signal(x, n_fft, step):
+def _prep_args(n_fft, step, zeropad):
     n_fft = int(n_fft)
     step = max(n_fft // 2, 1) if step is None else int(step)
+    zeropad = 1 if zeropad is None else int(zeropad)
+    return n_fft, step, zeropad
+
+
+def _stft_call(x, n_fft, step, window_name, zeropad, magnitude):
+    n_fft, step, zeropad = _prep_args(n_fft, step, zeropad)       # :62-63
     x = np.asarray(x)
     if x.ndim != 1:
-        raise ValueError('x must be 1D')
+        raise ValueError('x must be 1D')                          # :64-65
     if x.dtype.kind == 'c':
         raise ValueError('x must be real')
     if len(x) < 1:
         raise ValueError('x must not be empty')
-    return np.ascontiguousarray(x, dtype=np.float32), n_fft, step
-
-
-def _stft_call(x, n_fft, step, window_name, zeropad, magnitude):
-    x, n_fft, step = _prep_signal(x, n_fft, step)
-    zeropad = 1 if zeropad is None else int(zeropad)
+    # strided float32 column views (signal[:, ch] of an interleaved array) are passed as they are
+    keep, ptr, stride = _lib.f32_layout(x)
     L = _lib.lib()
     _lib.require_device()
     window = np.ascontiguousarray(dsp.get_window(window_name, n_fft), dtype=np.float32)   # :66
@@ -58,10 +60,37 @@ def _stft_call(x, n_fft, step, window_name, zeropad, magnitude):
     n_freqs = (n_fft * zeropad) // 2 + 1
     out = _lib.pinned_empty((n_frames, n_freqs), np.float32 if magnitude else np.complex64)
     flags = _lib.PAR_OUT_MAGNITUDE if magnitude else 0
-    rc = L.par_stft_f32(x.ctypes.data, len(x), 1, 1, 0, n_fft, step, zeropad, window.ctypes.data,
+    rc = L.par_stft_f32(ptr, len(x), stride, 1, 0, n_fft, step, zeropad, window.ctypes.data,
                         out.ctypes.data, n_freqs, 0, flags, _lib.device(), None)
     _lib.check(rc, "par_stft_f32")
+    del keep
     return out.T      # (n_freqs, n_frames), F-contiguous like the reference's numpy path (:147)
+
+
+def stft_multi(signal, n_fft=1024, step=512, window_name='blackmanharris', zeropad=1, magnitude=False):
+    """Extension (no reference counterpart): the transform of EVERY channel of a (frames, channels)
+    array in one library call / one upload.  Returns ``(channels, n_freqs, n_steps)``; ``out[c]``
+    equals ``stft(signal[:, c], ...)`` (or ``get_mag`` with ``magnitude=True``)."""
+    n_fft, step, zeropad = _prep_args(n_fft, step, zeropad)
+    signal = np.asarray(signal)
+    if signal.ndim != 2:
+        raise ValueError('signal must be (frames, channels)')
+    keep, ptr, fs, cs = _lib.f32_layout_2d(signal)
+    frames, channels = keep.shape
+    if frames < 1 or channels < 1:
+        raise ValueError('signal must not be empty')
+    L = _lib.lib()
+    _lib.require_device()
+    window = np.ascontiguousarray(dsp.get_window(window_name, n_fft), dtype=np.float32)
+    n_frames = int(L.par_stft_num_frames(frames, n_fft, step))
+    n_freqs = (n_fft * zeropad) // 2 + 1
+    out = _lib.pinned_empty((channels, n_frames, n_freqs), np.float32 if magnitude else np.complex64)
+    flags = _lib.PAR_OUT_MAGNITUDE if magnitude else 0
+    rc = L.par_stft_f32(ptr, frames, fs, channels, cs, n_fft, step, zeropad, window.ctypes.data,
+                        out.ctypes.data, n_freqs, n_frames * n_freqs, flags, _lib.device(), None)
+    _lib.check(rc, "par_stft_f32")
+    del keep
+    return out.transpose(0, 2, 1)
 
 
 def stft(x, n_fft=1024, step=512, window_name='blackmanharris', zeropad=1):

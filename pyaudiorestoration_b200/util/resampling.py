@@ -39,46 +39,47 @@ def find_cutoff(array, cutoff):
     return None
 
 
-def _channel_view(signal):
-    """(base array kept alive, pointer, n, element stride) of a 1-D float32 view; copies only
-    when the view is not expressible as a positive element stride."""
-    a = np.asarray(signal)
-    if a.ndim != 1:
-        raise ValueError("signal must be 1D")
-    if a.dtype != np.float32 or (len(a) > 1 and (a.strides[0] <= 0 or a.strides[0] % 4)):
-        a = np.ascontiguousarray(a, dtype=np.float32)
-    stride = a.strides[0] // 4 if len(a) > 1 else 1
-    return a, a.ctypes.data, len(a), max(stride, 1)
-
-
 def _resample_into(output, sample_at, signal, nt, sinc=True, aligned_edges=False):
-    """output[i] (1-D float32 view, any positive stride) = interpolated signal at sample_at[i]."""
+    """output[i] (1-D float32 view, any stride) = interpolated signal at sample_at[i].  The signal
+    view is passed as it lies in memory (strided column views are uploaded as one interleaved
+    span); a strided output goes through a contiguous pinned buffer."""
     L = _lib.lib()
     _lib.require_device()
     pos = np.ascontiguousarray(sample_at, dtype=np.float64)
-    sig, sig_ptr, n_in, sig_stride = _channel_view(signal)
+    keep, sig_ptr, sig_stride = _lib.f32_layout(signal)
+    n_in = len(keep)
     m = len(pos)
     if len(output) != m:
         raise ValueError("output and sample_at must have the same length")
-    out = output
-    direct = (isinstance(out, np.ndarray) and out.dtype == np.float32 and out.ndim == 1
-              and (m <= 1 or (out.strides[0] > 0 and out.strides[0] % 4 == 0)) and out.flags.writeable)
-    tmp = out if direct else np.empty(m, dtype=np.float32)
-    out_stride = max(tmp.strides[0] // 4, 1) if m > 1 else 1
+    direct = (isinstance(output, np.ndarray) and output.dtype == np.float32 and output.ndim == 1
+              and output.flags.c_contiguous and output.flags.writeable)
+    tmp = output if direct else _lib.pinned_empty((max(m, 1),), np.float32)[:m]
     if m:
         flags = _lib.PAR_SINC_ALIGNED_EDGES if aligned_edges else 0
         if sinc:
             rc = L.par_sinc_resample_f32(pos.ctypes.data, m, sig_ptr, n_in, sig_stride, 1, 0, int(nt),
-                                         tmp.ctypes.data, out_stride, 0, flags, _lib.device(), None)
+                                         tmp.ctypes.data, 1, 0, flags, _lib.device(), None)
             _lib.check(rc, "par_sinc_resample_f32")
         else:
             rc = L.par_linear_resample_f32(pos.ctypes.data, m, sig_ptr, n_in, sig_stride, 1, 0,
-                                           tmp.ctypes.data, out_stride, 0, 0, _lib.device(), None)
+                                           tmp.ctypes.data, 1, 0, 0, _lib.device(), None)
             _lib.check(rc, "par_linear_resample_f32")
     if not direct:
         output[:] = tmp
-    del sig
+    del keep
     return output
+
+
+def _channel_runs(signal, use_channels):
+    """Split the selected channels into runs of consecutive channel indices: each run is one
+    library call reading ``signal[:, c0:c0+k]`` in place."""
+    runs = []
+    for o, c in enumerate(use_channels):
+        if runs and runs[-1][1] + runs[-1][2] == c:
+            runs[-1][2] += 1
+        else:
+            runs.append([o, c, 1])
+    return runs
 
 
 # ------------------------------------------------------------------------------------ public API
@@ -147,45 +148,89 @@ def lag_to_pos(lag_curve, sr, num_input_samples):
     return sample_at
 
 
+def _mode_name(resampling_mode):
+    if resampling_mode not in ("Sinc", "Linear"):
+        raise ValueError(f"unknown resampling_mode {resampling_mode!r}")
+    return resampling_mode == "Sinc"
+
+
 def resample_channels(signal, sample_at, use_channels, resampling_mode="Sinc", sinc_quality=50, prog_sig=None):
-    """The "Resampling" phase of ``run`` (util/resampling.py:217-231) as a function:
-    ``signal`` (L, C) float32 -> ``(len(sample_at), len(use_channels))`` float32.  All selected
-    channels go through ONE library call (weights are computed once per output sample and applied
-    to every channel), so progress is reported once at the end of the phase."""
+    """The "Resampling" phase of ``run`` (util/resampling.py:217-231) for given read positions:
+    ``signal`` (L, C) float32 -> ``(len(sample_at), len(use_channels))`` float32, interleaved like the
+    reference's output array (:222).  Consecutive selected channels go through ONE library call:
+    the interleaved input is uploaded as it lies in memory, the tap weights of an output sample are
+    computed once and applied to every channel, and the kernel writes the interleaved output."""
     L = _lib.lib()
     _lib.require_device()
+    sinc = _mode_name(resampling_mode)
     signal = np.asarray(signal)
     if signal.ndim == 1:
         signal = signal[:, None]
-    if resampling_mode not in ("Sinc", "Linear"):
-        raise ValueError(f"unknown resampling_mode {resampling_mode!r}")
     use_channels = list(use_channels)
     num_channels = len(use_channels)
     m = len(sample_at)
-    # planar staging of the selected channels: (C_out, L) float32, pinned
-    n_in = signal.shape[0]
-    planar = _lib.pinned_empty((max(num_channels, 1), max(n_in, 1)), np.float32)
-    for o, c in enumerate(use_channels):
-        planar[o, :n_in] = signal[:, c]
-    out_planar = _lib.pinned_empty((max(num_channels, 1), max(m, 1)), np.float32)
+    output = _lib.pinned_empty((max(m, 1), max(num_channels, 1)), np.float32)[:m, :num_channels]
     pos = np.ascontiguousarray(sample_at, dtype=np.float64)
-    if m and num_channels:
-        if resampling_mode == "Sinc":
-            rc = L.par_sinc_resample_f32(pos.ctypes.data, m, planar.ctypes.data, n_in, 1, num_channels,
-                                         planar.shape[1], int(sinc_quality), out_planar.ctypes.data, 1,
-                                         out_planar.shape[1], 0, _lib.device(), None)
-            _lib.check(rc, "par_sinc_resample_f32")
-        else:
-            rc = L.par_linear_resample_f32(pos.ctypes.data, m, planar.ctypes.data, n_in, 1, num_channels,
-                                           planar.shape[1], out_planar.ctypes.data, 1, out_planar.shape[1],
-                                           0, _lib.device(), None)
-            _lib.check(rc, "par_linear_resample_f32")
-    output = np.empty((m, num_channels), dtype="float32")
-    for o in range(num_channels):
-        output[:, o] = out_planar[o, :m]
+    done = 0
+    for o, c0, k in _channel_runs(signal, use_channels):
+        keep, ptr, fs, cs = _lib.f32_layout_2d(signal[:, c0:c0 + k])
+        # a run that does not cover every output column goes through its own contiguous buffer
+        out = output if k == num_channels else _lib.pinned_empty((max(m, 1), k), np.float32)[:m]
+        if m:
+            args = (pos.ctypes.data, m, ptr, keep.shape[0], fs, k, cs)
+            tail = (out.ctypes.data, k, 1, 0, _lib.device(), None)
+            if sinc:
+                _lib.check(L.par_sinc_resample_f32(*args, int(sinc_quality), *tail), "par_sinc_resample_f32")
+            else:
+                _lib.check(L.par_linear_resample_f32(*args, *tail), "par_linear_resample_f32")
+        if out is not output:
+            output[:, o:o + k] = out
+        done += k
         if prog_sig:
-            prog_sig.notifyProgress.emit((o + 1) / num_channels * 100)
+            prog_sig.notifyProgress.emit(done / num_channels * 100)
     return output
+
+
+def varispeed(signal, sr, speed_curve, use_channels=None, resampling_mode="Sinc", sinc_quality=50, prog_sig=None):
+    """The "Preparing" + "Resampling" phases of ``run`` for a speed curve (util/resampling.py:181-184,
+    :217-231) in one library call per run of consecutive channels: the read positions are expanded on
+    the device (bit-identical to ``speed_to_pos``) and never copied to the host.
+    Returns the ``(M, len(use_channels))`` float32 output array."""
+    L = _lib.lib()
+    _lib.require_device()
+    sinc = _mode_name(resampling_mode)
+    signal = np.asarray(signal)
+    if signal.ndim == 1:
+        signal = signal[:, None]
+    if use_channels is None:
+        use_channels = range(signal.shape[1])
+    use_channels = list(use_channels)
+    num_channels = len(use_channels)
+    speed_curve = np.asarray(speed_curve, dtype=np.float64)
+    st = np.ascontiguousarray(speed_curve[:, 0] * sr)
+    sp = np.ascontiguousarray(speed_curve[:, 1])
+    k = len(st)
+    seg_n = np.empty(max(k - 1, 1), dtype=np.int64)
+    total = np.zeros(1, dtype=np.int64)
+    _lib.check(L.par_speed_segments(st.ctypes.data, sp.ctypes.data, k, seg_n.ctypes.data, total.ctypes.data),
+               "par_speed_segments")
+    cap = int(total[0])
+    full = _lib.pinned_empty((max(cap, 1), max(num_channels, 1)), np.float32)
+    m = np.zeros(1, dtype=np.int64)
+    done = 0
+    for o, c0, kk in _channel_runs(signal, use_channels):
+        keep, ptr, fs, cs = _lib.f32_layout_2d(signal[:, c0:c0 + kk])
+        out = full if kk == num_channels else _lib.pinned_empty((max(cap, 1), kk), np.float32)
+        rc = L.par_varispeed_f32(st.ctypes.data, sp.ctypes.data, k, ptr, keep.shape[0], fs, kk, cs,
+                                 _lib.PAR_MODE_SINC if sinc else _lib.PAR_MODE_LINEAR, int(sinc_quality),
+                                 out.ctypes.data, cap, kk, 1, m.ctypes.data, 0, _lib.device(), None)
+        _lib.check(rc, "par_varispeed_f32")
+        if out is not full:
+            full[:int(m[0]), o:o + kk] = out[:int(m[0])]
+        done += kk
+        if prog_sig:
+            prog_sig.notifyProgress.emit(done / max(num_channels, 1) * 100)
+    return full[:int(m[0]), :num_channels]
 
 
 def run(filenames, signal_data=None, speed_curve=None, resampling_mode="Linear", sinc_quality=50, use_channels=(),
@@ -206,21 +251,20 @@ def run(filenames, signal_data=None, speed_curve=None, resampling_mode="Linear",
             signal = np.asarray(signal)
             if signal.ndim == 1:
                 signal = signal[:, None]
-            if speed_curve is not None:
-                speed_curve = np.asarray(speed_curve)
-                sampletimes = speed_curve[:, 0] * sr
-                speeds = speed_curve[:, 1]
-                sample_at = speed_to_pos(sampletimes, speeds, len(signal))
-            elif lag_curve is not None:
+            sample_at = None
+            if speed_curve is None and lag_curve is not None:
                 sample_at = lag_to_pos(np.asarray(lag_curve), sr, len(signal))
-            else:
+            elif speed_curve is None:
                 raise ValueError("run needs a speed_curve or a lag_curve")
         if use_channels:
             channels = [channel for channel in use_channels if channel < signal.shape[1]]
         else:
             channels = tuple(range(signal.shape[1]))
         with log_duration("Resampling"):
-            output = resample_channels(signal, sample_at, channels, resampling_mode, sinc_quality, prog_sig)
+            if sample_at is None:
+                output = varispeed(signal, sr, speed_curve, channels, resampling_mode, sinc_quality, prog_sig)
+            else:
+                output = resample_channels(signal, sample_at, channels, resampling_mode, sinc_quality, prog_sig)
         with log_duration("Writing"):
             out_file_path = f"{os.path.splitext(filename)[0]}_res{suffix}.wav"
             io_ops.write_float_wav(out_file_path, output, sr)

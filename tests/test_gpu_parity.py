@@ -425,3 +425,52 @@ def test_device_pointer_calls_multichannel(par):
         assert rel_max(M[c], np.abs(truth) + 1e-7) <= TOL
         _check_sinc(out[c], ref_pos, xs[c], nt)
     assert L.par_kernel_launch_count() > 0
+
+
+# ----------------------------------------------------------------------------------------- in-place layouts / fused call
+def test_stft_multi_interleaved_matches_per_channel(fourier):
+    sig = np.stack([synth(30000, 41), synth(30000, 42), synth(30000, 43)], axis=1)      # (frames, channels)
+    multi = fourier.stft_multi(sig, 1024, 256)
+    assert multi.shape == (3, 513, 30000 // 256 + 1)
+    for c in range(3):
+        assert np.array_equal(multi[c], fourier.stft(sig[:, c], 1024, 256))
+        _check_stft(multi[c], np.ascontiguousarray(sig[:, c]), 1024, 256, "blackmanharris", 1)
+    mags = fourier.stft_multi(sig[:, ::2], 1024, 256, magnitude=True)                   # strided channel subset
+    assert np.array_equal(mags[1], fourier.get_mag(sig[:, 2], 1024, 256))
+    planar = np.ascontiguousarray(sig.T)
+    assert np.array_equal(fourier.stft_multi(planar.T, 1024, 256), multi)               # planar memory, same view
+
+
+@pytest.mark.parametrize("mode", ["Sinc", "Linear"])
+def test_varispeed_fused_matches_two_step(resampling, mode):
+    sr = 96000
+    sig = np.stack([synth(sr * 3, 51), synth(sr * 3, 52)], axis=1)
+    curve = wow_curve(3.0, sr, 1024, depth=0.02, freq=1.3)
+    out = resampling.varispeed(sig, sr, curve, None, mode, 50)
+    pos = oracle.speed_to_pos_c(curve[:, 0] * sr, curve[:, 1], len(sig))
+    assert out.shape == (len(pos), 2) and out.dtype == np.float32
+    two_step = resampling.resample_channels(sig, pos, [0, 1], mode, 50)
+    assert np.array_equal(out, two_step)
+    for c in range(2):
+        x = np.ascontiguousarray(sig[:, c])
+        if mode == "Sinc":
+            _check_sinc(np.ascontiguousarray(out[:, c]), pos, x, 50)
+        else:
+            assert np.array_equal(out[:, c], onp.linear_resample(pos, x))
+    # channel subsets / reordering go through per-run buffers
+    sub = resampling.varispeed(sig, sr, curve, [1], mode, 50)
+    assert np.array_equal(sub[:, 0], out[:, 1])
+    swapped = resampling.resample_channels(sig, pos, [1, 0], mode, 50)
+    assert np.array_equal(swapped[:, ::-1], out)
+
+
+def test_varispeed_capacity_error(par):
+    from pyaudiorestoration_b200 import _lib
+    L = _lib.lib()
+    st, sp = np.array([0.0, 8000.0]), np.array([0.5, 2.0])
+    x = synth(8000, 5)
+    out = np.zeros(100, np.float32)
+    m = np.zeros(1, np.int64)
+    rc = L.par_varispeed_f32(st.ctypes.data, sp.ctypes.data, 2, x.ctypes.data, 8000, 1, 1, 0, 1, 50,
+                             out.ctypes.data, 100, 1, 0, m.ctypes.data, 0, _lib.device(), None)
+    assert rc == _lib.PAR_ECAPACITY and m[0] == len(oracle.speed_to_pos_c(st, sp, 8000))
