@@ -128,7 +128,7 @@ int launch_expand_positions(const double *speeds_dev, const int64_t *seg_n_dev,
 // ------------------------------------------------------------------------------------------
 
 constexpr int SINC_TILE = 256;       // outputs per block iteration == threads per block
-constexpr int SINC_XPAD = 32;        // zero padding behind the staged span
+constexpr int SINC_XPAD = 32;        // zero padding behind the staged span (the last tap block may overhang)
 
 __device__ __forceinline__ float rcp_approx(float x) {
 	float r;
@@ -136,10 +136,29 @@ __device__ __forceinline__ float rcp_approx(float x) {
 	return r;
 }
 
-// sin/cos of pi * (phase / 2^63), phase a 64-bit fixed-point angle (wraps at one full turn)
+// sin/cos of the angle  pi * phase / 2^63  (phase wraps at one full turn = 2^64).
+// The top 32 bits are split into the nearest quarter turn and a residual in [-pi/4, pi/4) that is
+// converted to float32 (absolute error <= 5e-8 rad) and fed to Taylor polynomials whose truncation
+// error is < 2e-9 on that interval.
 __device__ __forceinline__ void sincos_fx(uint64_t phase, float *s, float *c) {
-	const int32_t top = (int32_t)(phase >> 32);
-	sincospif((float)top * 4.656612873077393e-10f /* 2^-31 */, s, c);
+	const uint32_t t = (uint32_t)(phase >> 32);
+	const uint32_t quad = (t + 0x20000000u) >> 30;
+	const int32_t res = (int32_t)(t - (quad << 30));
+	const float x = (float)res * 1.4629180792671596e-9f;      // pi / 2^31
+	const float x2 = x * x;
+	float ps = fmaf(x2, 2.7557319e-6f, -1.9841270e-4f);
+	ps = fmaf(x2, ps, 8.3333333e-3f);
+	ps = fmaf(x2, ps, -1.6666667e-1f);
+	const float sn = fmaf(x * x2, ps, x);
+	float pc = fmaf(x2, -2.7557319e-7f, 2.4801587e-5f);
+	pc = fmaf(x2, pc, -1.3888889e-3f);
+	pc = fmaf(x2, pc, 4.1666667e-2f);
+	pc = fmaf(x2, pc, -0.5f);
+	const float cs = fmaf(x2, pc, 1.0f);
+	const float a = (quad & 1) ? cs : sn;
+	const float b = (quad & 1) ? sn : cs;
+	*s = (quad & 2) ? -a : a;
+	*c = ((quad + 1) & 2) ? -b : b;
 }
 
 struct SampleSetup {
@@ -147,122 +166,183 @@ struct SampleSetup {
 	int cnt;           // number of taps (0 .. 2NT)
 	int koff;          // weight index of tap 0 (0 unless PAR_SINC_ALIGNED_EDGES at the start edge)
 	float s;           // fractional shift p - round(p), never exactly 0
-	bool lowpass;      // fc < 1
 	float fc;          // fc rounded to float32 (centre tap only)
+	bool lowpass;      // fc < 1
 	uint64_t f_fx;     // fc in units of 2^-63 half-turns
 	int64_t s_fx;      // fc * s in the same units
 };
 
-// Weights w[widx] for widx = 16*b .. 16*b+15 of one sample.
-template <bool LOWPASS>
-struct BlockWeights {
-	// fc == 1: w = c[widx] * sinpi(s) / (d - s); sinpi(s) is applied once at the end
-	// fc <  1: w = hp[widx] * sin(theta_b + j*pi*fc) / (d - s)
-	__device__ __forceinline__ static void run(const SampleSetup &su, int b, int nt,
-	                                           const float *__restrict__ tab, const float *cj,
-	                                           const float *sj, float (&w)[16]) {
-		const int d0 = 16 * b - nt;
-		float sa = 0.f, ca = 0.f;
-		if (LOWPASS) sincos_fx(su.f_fx * (uint64_t)(int64_t)d0 - (uint64_t)su.s_fx, &sa, &ca);
-		const float4 *t4 = reinterpret_cast<const float4 *>(tab + 16 * b);
-		float coef[16];
+// float64 part of util/resampling.py:67-84 for output i
+__device__ __forceinline__ SampleSetup sample_setup(const SincArgs &a, int64_t i) {
+	SampleSetup su;
+	const int nt = a.nt;
+	const double p = a.pos[i];
+	double per;
+	if (i + 1 < a.m) per = fmax(1e-12, a.pos[i + 1] - p);
+	else per = a.m >= 2 ? fmax(1e-12, a.pos[a.m - 1] - a.pos[a.m - 2]) : 0.0;
+	double fc = 1.0 / per;
+	if (!(fc < 1.0)) fc = 1.0;
+	double pr = rint(p);                        // half to even, like Python's round()
+	if (!(pr > -9.0e15)) pr = -9.0e15;          // NaN / -inf guard (garbage in, zeros out)
+	if (pr > 9.0e15) pr = 9.0e15;
+	const long long ind = (long long)pr;
+	const double sd = p - pr;
+	long long lower = ind - nt, upper = ind + nt;
+	if (lower < 0) lower = 0;
+	if (upper > a.n_in) upper = a.n_in;
+	su.lower = lower;
+	su.cnt = upper > lower ? (int)(upper - lower) : 0;
+	su.koff = a.aligned_edges ? (int)(lower - (ind - nt)) : 0;
+	float s = (float)sd;
+	if (s == 0.f) s = 1e-30f;
+	su.s = s;
+	su.lowpass = fc < 1.0;
+	su.fc = (float)fc;
+	su.f_fx = 0;
+	su.s_fx = 0;
+	if (su.lowpass) {
+		su.f_fx = __double2ull_rn(fc * 9223372036854775808.0);
+		su.s_fx = __double2ll_rn(fc * sd * 9223372036854775808.0);
+	}
+	return su;
+}
+
+// Per-sample rotation table of the fc < 1 path: (cos, sin)(j * pi * fc), j = 1 .. 15.
+// j = 1,2,3,4,8,12 are evaluated exactly from the fixed-point angle, the rest are one complex
+// product of two exact entries (absolute error ~1e-7).
+struct RotTable {
+	float c[16], s[16];
+	__device__ __forceinline__ void build(uint64_t f_fx) {
+		c[0] = 1.f; s[0] = 0.f;
 #pragma unroll
-		for (int v = 0; v < 4; v++) {
-			const float4 t = t4[v];
-			coef[4 * v] = t.x; coef[4 * v + 1] = t.y; coef[4 * v + 2] = t.z; coef[4 * v + 3] = t.w;
-		}
-		const bool far = d0 >= 16 || d0 + 15 <= -16;
-		const float base = (float)d0 - su.s;      // only used when every |q| of the block is >= 15.5
+		for (int j = 1; j <= 4; j++) sincos_fx(f_fx * (uint64_t)j, &s[j], &c[j]);
+		sincos_fx(f_fx * 8ull, &s[8], &c[8]);
+		sincos_fx(f_fx * 12ull, &s[12], &c[12]);
 #pragma unroll
-		for (int j = 0; j < 16; j++) {
-			const float q = far ? base + (float)j : (float)(d0 + j) - su.s;
-			float num = coef[j];
-			if (LOWPASS) {
-				// centre tap (|q| <= 0.5): the fixed-point angle has ABSOLUTE accuracy only, but the
-				// weight sin(pi fc q) / q needs RELATIVE accuracy as q -> 0
-				if (d0 == -j) num *= sinpif(su.fc * q);
-				else num *= fmaf(sa, cj[j], ca * sj[j]);
+		for (int hi = 4; hi <= 12; hi += 4) {
+#pragma unroll
+			for (int lo = 1; lo <= 3; lo++) {
+				c[hi + lo] = fmaf(c[hi], c[lo], -s[hi] * s[lo]);
+				s[hi + lo] = fmaf(s[hi], c[lo], c[hi] * s[lo]);
 			}
-			w[j] = num * rcp_approx(q);
 		}
 	}
 };
 
-template <int CH, bool LOWPASS, bool FAST, class XLoad>
-__device__ __forceinline__ void sinc_taps(const SampleSetup &su, int nt, int nblk,
-                                          const float *__restrict__ tab, XLoad xload,
+// One block of 16 taps (weight indices 16b .. 16b+15) of one output sample, all CH channels.
+// xrow points at the shared-memory sample that pairs with weight index 0 (channel-interleaved).
+//   fc == 1: w = c[widx] / (d - s)                      (sinpi(s) is applied once at the end)
+//   fc <  1: w = hp[widx] * sin(theta_b + j*pi*fc) / (d - s), theta_b exact per block
+template <int CH, bool LOWPASS, bool DESC>
+__device__ __forceinline__ void tap_block(const SampleSetup &su, int b, int nt, const float *__restrict__ tab,
+                                          const RotTable &rot, float centre_sn, const float *xrow,
                                           float (&acc)[CH]) {
-	float cj[16], sj[16];
-	if (LOWPASS) {
+	const int d0 = 16 * b - nt;
+	const bool near = d0 < 16 && d0 > -31;       // block holds a tap with |d| < 16
+	float sa = 0.f, ca = 0.f;
+	if (LOWPASS) sincos_fx(su.f_fx * (uint64_t)(int64_t)d0 - (uint64_t)su.s_fx, &sa, &ca);
+	const float base = (float)d0 - su.s;         // far blocks: |q| >= 15.5, one rounding is harmless
+	const float4 *t4 = reinterpret_cast<const float4 *>(tab + 16 * b);
 #pragma unroll
-		for (int j = 0; j < 16; j++) sincos_fx(su.f_fx * (uint64_t)j, &sj[j], &cj[j]);
+	for (int h = 0; h < 2; h++) {
+		const int hh = DESC ? 1 - h : h;
+		const float4 ta = __ldg(t4 + 2 * hh), tb = __ldg(t4 + 2 * hh + 1);
+		const float coef[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+		float w[8];
+#pragma unroll
+		for (int u = 0; u < 8; u++) {
+			const int j = 8 * hh + u;
+			const float q = near ? (float)(d0 + j) - su.s : base + (float)j;
+			float num = coef[u];
+			if (LOWPASS) {
+				float sn = fmaf(sa, rot.c[j], ca * rot.s[j]);
+				// centre tap (|q| <= 0.5): the fixed-point angle has ABSOLUTE accuracy only, but
+				// sin(pi fc q) / q needs RELATIVE accuracy as q -> 0
+				if (near && d0 == -j) sn = centre_sn;
+				num *= sn;
+			}
+			w[u] = num * rcp_approx(q);
+		}
+#pragma unroll
+		for (int u = 0; u < 8; u++) {
+			const int uu = DESC ? 7 - u : u;
+			const float *xp = xrow + (16 * b + 8 * hh + uu) * CH;
+			if (CH == 1) {
+				acc[0] = fmaf(xp[0], w[uu], acc[0]);
+			} else if (CH == 2) {
+				const float2 v = *reinterpret_cast<const float2 *>(xp);
+				acc[0] = fmaf(v.x, w[uu], acc[0]);
+				acc[1] = fmaf(v.y, w[uu], acc[1]);
+			} else {
+#pragma unroll
+				for (int c4 = 0; c4 < CH; c4 += 4) {
+					const float4 v = *reinterpret_cast<const float4 *>(xp + c4);
+					acc[c4] = fmaf(v.x, w[uu], acc[c4]);
+					acc[c4 + 1] = fmaf(v.y, w[uu], acc[c4 + 1]);
+					acc[c4 + 2] = fmaf(v.z, w[uu], acc[c4 + 2]);
+					acc[c4 + 3] = fmaf(v.w, w[uu], acc[c4 + 3]);
+				}
+			}
+		}
 	}
-	// Summation order: the weights decay like 1/|d| away from the centre tap, so each half of the
-	// tap run is accumulated from its far end towards the centre (small terms first) in its own
-	// accumulator; a plain left-to-right float32 sum costs ~1e-6 relative at NT >= 128.
+}
+
+// All 2*NT taps of an interior output sample whose inputs are staged in shared memory.
+// Summation order: the weights decay like 1/|d| away from the centre tap, so each half of the tap
+// run is accumulated from its far end towards the centre (small terms first) in its own
+// accumulator; a plain left-to-right float32 sum costs ~1e-6 relative at NT >= 128.
+template <int CH, bool LOWPASS>
+__device__ __forceinline__ void taps_fast(const SampleSetup &su, int nt, int nblk, const float *__restrict__ tab,
+                                          const float *xrow, float (&out)[CH]) {
+	RotTable rot;
+	float centre_sn = 0.f;
+	if (LOWPASS) {
+		rot.build(su.f_fx);
+		centre_sn = sinpif(su.fc * (0.f - su.s));     // numerator of the d = 0 tap, q = -s
+	}
 	float accl[CH], accr[CH];
 #pragma unroll
 	for (int c = 0; c < CH; c++) accl[c] = accr[c] = 0.f;
 	const int half = nblk >> 1;
-	for (int it = 0; it < nblk; it++) {
-		const bool right = it & 1;
-		const int b = right ? nblk - 1 - (it >> 1) : (it >> 1);
-		// odd block count: the middle block is visited last, on the left accumulator
-		float w[16];
-		BlockWeights<LOWPASS>::run(su, b, nt, tab, cj, sj, w);
-		if (right && b >= half) {
-#pragma unroll
-			for (int j = 15; j >= 0; j--) {
-				const int k = 16 * b + j - su.koff;
-				if (FAST) {
-#pragma unroll
-					for (int c = 0; c < CH; c++) accr[c] = fmaf(xload(c, k), w[j], accr[c]);
-				} else {
-					const bool on = k >= 0 && k < su.cnt;
-#pragma unroll
-					for (int c = 0; c < CH; c++) accr[c] = fmaf(on ? xload(c, k) : 0.f, on ? w[j] : 0.f, accr[c]);
-				}
-			}
-		} else {
-#pragma unroll
-			for (int j = 0; j < 16; j++) {
-				const int k = 16 * b + j - su.koff;      // tap number; its sample is lower + k
-				if (FAST) {
-#pragma unroll
-					for (int c = 0; c < CH; c++) accl[c] = fmaf(xload(c, k), w[j], accl[c]);
-				} else {
-					const bool on = k >= 0 && k < su.cnt;
-#pragma unroll
-					for (int c = 0; c < CH; c++) accl[c] = fmaf(on ? xload(c, k) : 0.f, on ? w[j] : 0.f, accl[c]);
-				}
-			}
-		}
+	for (int it = 0; it < half; it++) {
+		tap_block<CH, LOWPASS, false>(su, it, nt, tab, rot, centre_sn, xrow, accl);
+		tap_block<CH, LOWPASS, true>(su, nblk - 1 - it, nt, tab, rot, centre_sn, xrow, accr);
 	}
+	if (nblk & 1) tap_block<CH, LOWPASS, false>(su, half, nt, tab, rot, centre_sn, xrow, accl);
 #pragma unroll
-	for (int c = 0; c < CH; c++) acc[c] = accl[c] + accr[c];
+	for (int c = 0; c < CH; c++) out[c] = accl[c] + accr[c];
 }
 
-struct SmemX {
-	const float *xs;
-	int plane, off;   // plane stride, offset of tap 0's sample
-	__device__ __forceinline__ float operator()(int c, int k) const { return xs[c * plane + off + k]; }
-};
-struct GlobalX {
-	const float *x;   // first channel of the group
-	int64_t ch_stride, stride, lower;
-	__device__ __forceinline__ float operator()(int c, int k) const {
-		return __ldg(x + c * ch_stride + (lower + k) * stride);
-	}
-};
+// Weight of weight-index widx, any sample (edge / fallback path).
+__device__ __forceinline__ float weight_single(const SampleSetup &su, int widx, int nt,
+                                               const float *__restrict__ ctab, const float *__restrict__ hptab) {
+	const int d = widx - nt;
+	const float q = (float)d - su.s;
+	if (!su.lowpass) return __ldg(ctab + widx) * rcp_approx(q);
+	float sn, cs;
+	if (d == 0) sn = sinpif(su.fc * q);
+	else sincos_fx(su.f_fx * (uint64_t)(int64_t)d - (uint64_t)su.s_fx, &sn, &cs);
+	return __ldg(hptab + widx) * sn * rcp_approx(q);
+}
+
+// Edge / fallback path: any tap count, samples read from global memory, same summation order.
+__device__ __forceinline__ float taps_slow(const SampleSetup &su, int nt, const float *__restrict__ ctab,
+                                           const float *__restrict__ hptab, const float *__restrict__ x,
+                                           int64_t stride) {
+	float accl = 0.f, accr = 0.f;
+	const int mid = min(max(nt - su.koff, 0), su.cnt);       // taps [0, mid) lie left of the centre
+	for (int k = 0; k < mid; k++)
+		accl = fmaf(__ldg(x + (su.lower + k) * stride), weight_single(su, k + su.koff, nt, ctab, hptab), accl);
+	for (int k = su.cnt - 1; k >= mid; k--)
+		accr = fmaf(__ldg(x + (su.lower + k) * stride), weight_single(su, k + su.koff, nt, ctab, hptab), accr);
+	return accl + accr;
+}
 
 template <int CH>
-__global__ void __launch_bounds__(SINC_TILE)
-sinc_kernel(SincArgs a, const float *__restrict__ ctab, const float *__restrict__ hptab, int nblk,
-            int span_cap) {
-	extern __shared__ float xs[];        // CH planes of span_cap + SINC_XPAD floats
+__global__ void __launch_bounds__(SINC_TILE, 2)
+sinc_kernel(SincArgs a, const float *__restrict__ ctab, const float *__restrict__ hptab, int nblk, int span_cap) {
+	extern __shared__ __align__(16) float xs[];      // (span_cap + SINC_XPAD) samples x CH, channel-interleaved
 	__shared__ long long red_lo[SINC_TILE / 32], red_hi[SINC_TILE / 32];
-	__shared__ long long tile_lo, tile_hi;
-	const int plane = span_cap + SINC_XPAD;
 	const int nt = a.nt;
 	const int64_t tiles = (a.m + SINC_TILE - 1) / SINC_TILE;
 	const int groups = (a.n_ch + CH - 1) / CH;
@@ -276,40 +356,14 @@ sinc_kernel(SincArgs a, const float *__restrict__ ctab, const float *__restrict_
 		const int64_t i = tile * SINC_TILE + threadIdx.x;
 		const bool live = i < a.m;
 
-		// ---- per-sample setup in float64 (util/resampling.py:67-84) ----
 		SampleSetup su;
-		su.lower = 0; su.cnt = 0; su.koff = 0; su.s = 1e-30f; su.lowpass = false; su.fc = 1.f; su.f_fx = 0; su.s_fx = 0;
+		su.lower = 0; su.cnt = 0; su.koff = 0; su.s = 1e-30f; su.fc = 1.f; su.lowpass = false; su.f_fx = 0; su.s_fx = 0;
 		long long lo = LLONG_MAX, hi = LLONG_MIN;
 		if (live) {
-			const double p = a.pos[i];
-			double per;
-			if (i + 1 < a.m) per = fmax(1e-12, a.pos[i + 1] - p);
-			else per = a.m >= 2 ? fmax(1e-12, a.pos[a.m - 1] - a.pos[a.m - 2]) : 0.0;
-			double fc = 1.0 / per;
-			if (!(fc < 1.0)) fc = 1.0;
-			double pr = rint(p);
-			if (!(pr > -9.0e15)) pr = -9.0e15;      // NaN / -inf guard (garbage in, zeros out)
-			if (pr > 9.0e15) pr = 9.0e15;
-			const long long ind = (long long)pr;
-			const double sd = p - pr;
-			long long lower = ind - nt, upper = ind + nt;
-			if (lower < 0) lower = 0;
-			if (upper > a.n_in) upper = a.n_in;
-			su.lower = lower;
-			su.cnt = upper > lower ? (int)(upper - lower) : 0;
-			if (a.aligned_edges) su.koff = (int)(lower - (ind - nt));
-			float s = (float)sd;
-			if (s == 0.f) s = 1e-30f;
-			su.s = s;
-			su.lowpass = fc < 1.0;
-			if (su.lowpass) {
-				su.fc = (float)fc;
-				su.f_fx = __double2ull_rn(fc * 9223372036854775808.0);
-				su.s_fx = __double2ll_rn(fc * sd * 9223372036854775808.0);
-			}
-			if (su.cnt > 0) { lo = lower; hi = upper; }
+			su = sample_setup(a, i);
+			if (su.cnt > 0) { lo = su.lower; hi = su.lower + su.cnt; }
 		}
-		// ---- tile span ----
+		// ---- input span of the tile ----
 #pragma unroll
 		for (int o = 16; o > 0; o >>= 1) {
 			lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
@@ -317,23 +371,20 @@ sinc_kernel(SincArgs a, const float *__restrict__ ctab, const float *__restrict_
 		}
 		if (lane == 0) { red_lo[warp] = lo; red_hi[warp] = hi; }
 		__syncthreads();
-		if (threadIdx.x == 0) {
-			long long l = red_lo[0], h = red_hi[0];
-			for (int w = 1; w < SINC_TILE / 32; w++) { l = min(l, red_lo[w]); h = max(h, red_hi[w]); }
-			tile_lo = l; tile_hi = h;
-		}
-		__syncthreads();
-		const long long tlo = tile_lo, thi = tile_hi;
+		long long tlo = red_lo[0], thi = red_hi[0];
+#pragma unroll
+		for (int w = 1; w < SINC_TILE / 32; w++) { tlo = min(tlo, red_lo[w]); thi = max(thi, red_hi[w]); }
 		const bool any = thi > tlo;
 		const bool staged = any && (thi - tlo) <= span_cap;
 		if (staged) {
-			const int span = (int)(thi - tlo);
-			for (int c = 0; c < CH; c++) {
-				const bool chv = ch0 + c < a.n_ch;
-				const float *src = a.signal + (int64_t)(ch0 + c) * a.sig_ch_stride;
-				float *dst = xs + c * plane;
-				for (int e = threadIdx.x; e < span + SINC_XPAD; e += SINC_TILE)
-					dst[e] = (chv && e < span) ? __ldg(src + (tlo + e) * a.sig_stride) : 0.f;
+			const int total = ((int)(thi - tlo) + SINC_XPAD) * CH;
+			const int valid = (int)(thi - tlo);
+			for (int idx = threadIdx.x; idx < total; idx += SINC_TILE) {
+				const int e = idx / CH, c = idx - e * CH;
+				float v = 0.f;
+				if (e < valid && ch0 + c < a.n_ch)
+					v = __ldg(a.signal + (int64_t)(ch0 + c) * a.sig_ch_stride + (tlo + e) * a.sig_stride);
+				xs[idx] = v;
 			}
 		}
 		__syncthreads();
@@ -341,31 +392,20 @@ sinc_kernel(SincArgs a, const float *__restrict__ ctab, const float *__restrict_
 		float acc[CH];
 #pragma unroll
 		for (int c = 0; c < CH; c++) acc[c] = 0.f;
-		if (any) {
-			const bool interior = su.cnt == 2 * nt && su.koff == 0;
-			const bool warp_fast = staged && __all_sync(0xffffffffu, interior || !live);
-			const float *tab = su.lowpass ? hptab : ctab;
-			if (staged) {
-				SmemX xl{xs, plane, (int)(su.lower - tlo)};
-				if (!live || su.cnt == 0) {
-					// nothing
-				} else if (warp_fast) {
-					if (su.lowpass) sinc_taps<CH, true, true>(su, nt, nblk, tab, xl, acc);
-					else sinc_taps<CH, false, true>(su, nt, nblk, tab, xl, acc);
-				} else {
-					if (su.lowpass) sinc_taps<CH, true, false>(su, nt, nblk, tab, xl, acc);
-					else sinc_taps<CH, false, false>(su, nt, nblk, tab, xl, acc);
-				}
-			} else if (live && su.cnt > 0) {
-				// span too wide for shared memory (wildly non-monotone positions): read through L1/L2
-				for (int c = 0; c < CH; c++) {
-					if (ch0 + c >= a.n_ch) break;
-					GlobalX xl{a.signal + (int64_t)(ch0 + c) * a.sig_ch_stride, 0, a.sig_stride, su.lower};
-					float one[1];
-					if (su.lowpass) sinc_taps<1, true, false>(su, nt, nblk, tab, xl, one);
-					else sinc_taps<1, false, false>(su, nt, nblk, tab, xl, one);
-					acc[c] = one[0];
-				}
+		const bool interior = su.cnt == 2 * nt && su.koff == 0;
+		const bool warp_fast = staged && __all_sync(0xffffffffu, interior || !live || su.cnt == 0);
+		if (live && su.cnt > 0) {
+			if (warp_fast) {
+				const float *xrow = xs + (int)(su.lower - tlo) * CH;
+				if (su.lowpass) taps_fast<CH, true>(su, nt, nblk, hptab, xrow, acc);
+				else taps_fast<CH, false>(su, nt, nblk, ctab, xrow, acc);
+			} else {
+				// first / last NT outputs of a file, or a span too wide for shared memory
+#pragma unroll
+				for (int c = 0; c < CH; c++)
+					if (ch0 + c < a.n_ch)
+						acc[c] = taps_slow(su, nt, ctab, hptab, a.signal + (int64_t)(ch0 + c) * a.sig_ch_stride,
+						                   a.sig_stride);
 			}
 			if (!su.lowpass) {
 				const float sp = sinpif(su.s);
@@ -408,6 +448,7 @@ int launch_sinc(const SincArgs &a, int device, cudaStream_t st) {
 	SincTables tb;
 	int rc = sinc_tables(device, a.nt, st, &tb);
 	if (rc != PAR_OK) return rc;
+	if (a.n_ch >= 4) return launch_sinc_ch<4>(a, device, st, tb);
 	if (a.n_ch >= 2) return launch_sinc_ch<2>(a, device, st, tb);
 	return launch_sinc_ch<1>(a, device, st, tb);
 }
