@@ -3,6 +3,7 @@
 // speed_to_pos.  No CPU implementation of any kernel lives here: without a CUDA device every
 // compute entry fails with PAR_ECUDA.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -164,6 +165,19 @@ static int use_device(int device) {
 	}
 	if (device < 0 || device >= n) { set_error("device index out of range"); return PAR_EINVAL; }
 	PAR_CUDA(cudaSetDevice(device));
+	// Scratch comes from the stream-ordered pool; keep freed blocks cached instead of handing them
+	// back to the driver at every synchronisation (the default release threshold is 0, which turns
+	// each host-pointer call into a fresh multi-GB allocation).
+	static std::atomic<uint64_t> pool_ready{0};
+	if (device < 64 && !(pool_ready.load() & (1ull << device))) {
+		cudaMemPool_t pool;
+		if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+			uint64_t keep = UINT64_MAX;
+			cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+		}
+		cudaGetLastError();
+		pool_ready.fetch_or(1ull << device);
+	}
 	return PAR_OK;
 }
 
@@ -198,48 +212,105 @@ struct EventTimer {
 };
 
 // ---- host <-> device staging of audio ---------------------------------------------------------
-// A host channel set (n samples, element stride `stride`, channel c at +c*ch_stride) is uploaded
-//  (a) planar, one contiguous copy per channel, when stride == 1;
-//  (b) as ONE contiguous copy of the whole interleaved span when the channels interleave inside
-//      the sample stride (the reference's (frames, channels) arrays and column views of them) and the
-//      span is at most 4x the useful bytes -- the kernels then read it with the host's strides;
+// Helper streams of a host-pointer call: uploads, kernels and downloads of successive chunks
+// overlap (H2D and D2H are separate copy engines; PCIe is full duplex).  Declared AFTER the
+// DevBufs of a call so that it is destroyed (and its streams drained) BEFORE they are freed.
+struct SideStreams {
+	cudaStream_t up = nullptr, down = nullptr;
+	std::vector<cudaEvent_t> evs;
+	int init() {
+		PAR_CUDA(cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
+		PAR_CUDA(cudaStreamCreateWithFlags(&down, cudaStreamNonBlocking));
+		return PAR_OK;
+	}
+	// event recorded on `on`
+	int mark(cudaStream_t on, cudaEvent_t *e) {
+		PAR_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+		evs.push_back(*e);
+		PAR_CUDA(cudaEventRecord(*e, on));
+		return PAR_OK;
+	}
+	int after(cudaStream_t waiter, cudaStream_t on) {
+		cudaEvent_t e;
+		int rc = mark(on, &e);
+		if (rc != PAR_OK) return rc;
+		PAR_CUDA(cudaStreamWaitEvent(waiter, e, 0));
+		return PAR_OK;
+	}
+	int drain() {
+		if (up) PAR_CUDA(cudaStreamSynchronize(up));
+		if (down) PAR_CUDA(cudaStreamSynchronize(down));
+		return PAR_OK;
+	}
+	~SideStreams() {
+		if (up) cudaStreamSynchronize(up);
+		if (down) cudaStreamSynchronize(down);
+		for (cudaEvent_t e : evs) cudaEventDestroy(e);
+		if (up) cudaStreamDestroy(up);
+		if (down) cudaStreamDestroy(down);
+	}
+};
+
+// A host channel set (n samples, element stride `stride`, channel c at +c*ch_stride), uploaded
+// progressively in sample order:
+//  (a) planar, one contiguous copy per channel and piece, when stride == 1;
+//  (b) as contiguous pieces of the whole interleaved span when the channels interleave inside the
+//      sample stride (the reference's (frames, channels) arrays and column views of them) and the
+//      span is at most 4x the useful bytes -- kernels then read it with the host's strides;
 //  (c) with a strided 2-D copy per channel otherwise (slow, correct).
 struct DevAudio {
 	float *p = nullptr;
 	int64_t stride = 1, ch_stride = 0;
 };
 
-static int upload_audio(DevBuf &buf, const float *src, int64_t n, int64_t stride, int n_ch, int64_t ch_stride,
-                        cudaStream_t st, DevAudio *out) {
-	int rc;
-	const int64_t n_al = ((n > 0 ? n : 1) + 3) & ~(int64_t)3;
-	const int64_t span = (n - 1) * stride + (int64_t)(n_ch - 1) * ch_stride + 1;
-	const bool interleaved = stride > 1 && (n_ch == 1 || (ch_stride > 0 && ch_stride < stride)) &&
-	                         span <= 4 * n * (int64_t)n_ch + 64;
-	if (n <= 0) {
-		if ((rc = buf.alloc(16)) != PAR_OK) return rc;
-		out->p = buf.as<float>(); out->stride = 1; out->ch_stride = 0;
-		return PAR_OK;
+struct AudioUploader {
+	const float *src = nullptr;
+	int64_t n = 0, stride = 1, ch_stride = 0, n_al = 4, span = 0, done = 0;
+	int n_ch = 1;
+	bool interleaved = false;
+	DevBuf raw;
+	explicit AudioUploader(cudaStream_t st) : raw(st) {}
+
+	int init(const float *src_, int64_t n_, int64_t stride_, int n_ch_, int64_t ch_stride_) {
+		src = src_; n = n_; stride = stride_; n_ch = n_ch_; ch_stride = ch_stride_;
+		n_al = ((n > 0 ? n : 1) + 3) & ~(int64_t)3;
+		span = n > 0 ? (n - 1) * stride + (int64_t)(n_ch - 1) * ch_stride + 1 : 0;
+		interleaved = n > 0 && stride > 1 && (n_ch == 1 || (ch_stride > 0 && ch_stride < stride)) &&
+		              span <= 4 * n * (int64_t)n_ch + 64;
+		return raw.alloc((size_t)((interleaved ? span + 4 : n_al * n_ch) + 4) * sizeof(float));
 	}
-	if (interleaved) {
-		if ((rc = buf.alloc((size_t)(span + 4) * sizeof(float))) != PAR_OK) return rc;
-		PAR_CUDA(cudaMemcpyAsync(buf.p, src, (size_t)span * sizeof(float), cudaMemcpyHostToDevice, st));
-		out->p = buf.as<float>(); out->stride = stride; out->ch_stride = ch_stride;
-		return PAR_OK;
+	DevAudio view() const {
+		DevAudio v;
+		v.p = (float *)raw.p;
+		if (interleaved) { v.stride = stride; v.ch_stride = ch_stride; }
+		else { v.stride = 1; v.ch_stride = n_al; }
+		return v;
 	}
-	if ((rc = buf.alloc((size_t)n_al * n_ch * sizeof(float))) != PAR_OK) return rc;
-	for (int c = 0; c < n_ch; c++) {
-		float *dst = buf.as<float>() + c * n_al;
-		if (stride == 1) {
-			PAR_CUDA(cudaMemcpyAsync(dst, src + c * ch_stride, n * sizeof(float), cudaMemcpyHostToDevice, st));
+	// enqueue on `up` the copy of samples [done, hi)
+	int upload_to(int64_t hi, cudaStream_t up) {
+		if (hi > n) hi = n;
+		if (hi <= done) return PAR_OK;
+		float *d = (float *)raw.p;
+		if (interleaved) {
+			const int64_t a = done * stride;
+			const int64_t b = hi == n ? span : hi * stride;
+			PAR_CUDA(cudaMemcpyAsync(d + a, src + a, (size_t)(b - a) * sizeof(float), cudaMemcpyHostToDevice, up));
 		} else {
-			PAR_CUDA(cudaMemcpy2DAsync(dst, sizeof(float), src + c * ch_stride, stride * sizeof(float),
-			                           sizeof(float), n, cudaMemcpyHostToDevice, st));
+			for (int c = 0; c < n_ch; c++) {
+				if (stride == 1) {
+					PAR_CUDA(cudaMemcpyAsync(d + c * n_al + done, src + c * ch_stride + done,
+					                         (size_t)(hi - done) * sizeof(float), cudaMemcpyHostToDevice, up));
+				} else {
+					PAR_CUDA(cudaMemcpy2DAsync(d + c * n_al + done, sizeof(float), src + c * ch_stride + done * stride,
+					                           stride * sizeof(float), sizeof(float), hi - done,
+					                           cudaMemcpyHostToDevice, up));
+				}
+			}
 		}
+		done = hi;
+		return PAR_OK;
 	}
-	out->p = buf.as<float>(); out->stride = 1; out->ch_stride = n_al;
-	return PAR_OK;
-}
+};
 
 // Device-side image of a host output channel set.  When the channels tile the host span exactly
 // (fully interleaved: ch_stride 1, stride n_ch; or one contiguous channel) the kernel writes the
@@ -264,23 +335,38 @@ static int alloc_out(DevBuf &buf, int64_t m, int64_t stride, int n_ch, int64_t c
 	return PAR_OK;
 }
 
-static int download_out(const DevOut &o, float *dst, int64_t m, int64_t stride, int n_ch, int64_t ch_stride,
-                        cudaStream_t st) {
-	if (m <= 0) return PAR_OK;
+// copy output samples [o0, o1) of every channel back to the host
+static int download_out(const DevOut &o, float *dst, int64_t o0, int64_t o1, int64_t stride, int n_ch,
+                        int64_t ch_stride, cudaStream_t st) {
+	if (o1 <= o0) return PAR_OK;
+	const int64_t cnt = o1 - o0;
 	if (o.image) {
-		PAR_CUDA(cudaMemcpyAsync(dst, o.p, (size_t)m * n_ch * sizeof(float), cudaMemcpyDeviceToHost, st));
+		PAR_CUDA(cudaMemcpyAsync(dst + o0 * n_ch, o.p + o0 * n_ch, (size_t)cnt * n_ch * sizeof(float),
+		                         cudaMemcpyDeviceToHost, st));
 		return PAR_OK;
 	}
 	for (int c = 0; c < n_ch; c++) {
 		if (stride == 1) {
-			PAR_CUDA(cudaMemcpyAsync(dst + c * ch_stride, o.p + c * o.ch_stride, m * sizeof(float),
+			PAR_CUDA(cudaMemcpyAsync(dst + c * ch_stride + o0, o.p + c * o.ch_stride + o0, cnt * sizeof(float),
 			                         cudaMemcpyDeviceToHost, st));
 		} else {
-			PAR_CUDA(cudaMemcpy2DAsync(dst + c * ch_stride, stride * sizeof(float), o.p + c * o.ch_stride,
-			                           sizeof(float), sizeof(float), m, cudaMemcpyDeviceToHost, st));
+			PAR_CUDA(cudaMemcpy2DAsync(dst + c * ch_stride + o0 * stride, stride * sizeof(float),
+			                           o.p + c * o.ch_stride + o0, sizeof(float), sizeof(float), cnt,
+			                           cudaMemcpyDeviceToHost, st));
 		}
 	}
 	return PAR_OK;
+}
+
+// bytes of output per pipeline chunk of a host-pointer call ($PAR_B200_CHUNK_BYTES overrides; tests
+// use it to push small inputs through many chunks)
+static int64_t chunk_bytes() {
+	const char *e = getenv("PAR_B200_CHUNK_BYTES");
+	if (e && *e) {
+		const long long v = atoll(e);
+		if (v >= 4096) return v;
+	}
+	return 48ll << 20;
 }
 
 }  // namespace par
@@ -335,42 +421,64 @@ PAR_API int par_stft_f32(const float *x, int64_t n, int64_t x_stride, int n_ch, 
 	const bool mag = flags & PAR_OUT_MAGNITUDE;
 	StftArgs a;
 	a.n = n; a.n_ch = n_ch; a.n_fft = n_fft; a.hop = hop; a.zeropad = zeropad; a.n_frames = T;
-	a.window = dwin; a.magnitude = mag ? 1 : 0;
+	a.window = dwin; a.magnitude = mag ? 1 : 0; a.frame0 = 0;
 	if (flags & PAR_DEVICE_PTRS) {
 		a.x = x; a.x_stride = x_stride; a.x_ch_stride = x_ch_stride;
 		a.out = out; a.out_pitch = out_pitch; a.out_ch_stride = out_ch_stride;
 		return launch_stft(a, device, st);
 	}
-	// host pointers: upload (in the host's own layout), de-interleave on the device if needed, run,
-	// copy the rows back
+	// host pointers: chunks of frames flow through upload -> (de-interleave) -> transform -> download
+	// on three streams, so the PCIe copies in both directions overlap each other and the kernels
 	const size_t esz = mag ? sizeof(float) : sizeof(float2);
-	const int64_t n_al = (n + 3) & ~(int64_t)3;
-	DevBuf dx(st), dplanar(st), dout(st);
-	DevAudio da;
-	if ((rc = upload_audio(dx, x, n, x_stride, n_ch, x_ch_stride, st, &da)) != PAR_OK) return rc;
+	DevBuf dplanar(st), dout(st);
+	AudioUploader up(st);
+	SideStreams ss;
+	if ((rc = up.init(x, n, x_stride, n_ch, x_ch_stride)) != PAR_OK) return rc;
 	if ((rc = dout.alloc((size_t)T * F * n_ch * esz)) != PAR_OK) return rc;
+	const DevAudio da = up.view();
+	if (up.interleaved && (rc = dplanar.alloc((size_t)up.n_al * n_ch * sizeof(float))) != PAR_OK) return rc;
+	if ((rc = ss.init()) != PAR_OK) return rc;
+	if ((rc = ss.after(ss.up, st)) != PAR_OK) return rc;       // allocations are stream-ordered on st
+	if (up.interleaved) { a.x = dplanar.as<float>(); a.x_stride = 1; a.x_ch_stride = up.n_al; }
+	else { a.x = da.p; a.x_stride = 1; a.x_ch_stride = da.ch_stride; }
+	a.out = dout.p; a.out_pitch = F; a.out_ch_stride = T * F;
+	int64_t per_chunk = chunk_bytes() / (int64_t)(F * esz * n_ch);
+	if (per_chunk < 16) per_chunk = 16;
+	const int64_t half = n_fft / 2;
 	EventTimer tm(st);
 	tm.start();
-	if (da.stride != 1) {
-		if ((rc = dplanar.alloc((size_t)n_al * n_ch * sizeof(float))) != PAR_OK) return rc;
-		if ((rc = launch_deinterleave(da.p, n, da.stride, n_ch, da.ch_stride, dplanar.as<float>(), n_al, device, st)) != PAR_OK)
-			return rc;
-		a.x = dplanar.as<float>(); a.x_stride = 1; a.x_ch_stride = n_al;
-	} else {
-		a.x = da.p; a.x_stride = 1; a.x_ch_stride = da.ch_stride;
-	}
-	a.out = dout.p; a.out_pitch = F; a.out_ch_stride = T * F;
-	if ((rc = launch_stft(a, device, st)) != PAR_OK) return rc;
-	tm.stop();
-	for (int c = 0; c < n_ch; c++) {
-		char *dst = (char *)out + (size_t)c * out_ch_stride * esz;
-		const char *src = (const char *)dout.p + (size_t)c * T * F * esz;
-		if (out_pitch == F) {
-			PAR_CUDA(cudaMemcpyAsync(dst, src, (size_t)T * F * esz, cudaMemcpyDeviceToHost, st));
-		} else {
-			PAR_CUDA(cudaMemcpy2DAsync(dst, out_pitch * esz, src, F * esz, F * esz, T, cudaMemcpyDeviceToHost, st));
+	int64_t planar_done = 0;
+	for (int64_t t0 = 0; t0 < T; t0 += per_chunk) {
+		const int64_t t1 = t0 + per_chunk < T ? t0 + per_chunk : T;
+		// samples the frames [t0, t1) read: up to (t1-1)*hop - half + n_fft, everything once a frame
+		// reaches the reflected tail (or the signal is short enough to reflect more than once)
+		int64_t need = (t1 - 1) * hop - half + n_fft + 8;
+		if (need >= n - 1 || n <= 2 * (int64_t)n_fft) need = n;
+		if ((rc = up.upload_to(need, ss.up)) != PAR_OK) return rc;
+		if ((rc = ss.after(st, ss.up)) != PAR_OK) return rc;
+		if (up.interleaved && need > planar_done) {
+			rc = launch_deinterleave(da.p + planar_done * da.stride, need - planar_done, da.stride, n_ch, da.ch_stride,
+			                         dplanar.as<float>() + planar_done, up.n_al, device, st);
+			if (rc != PAR_OK) return rc;
+			planar_done = need;
+		}
+		a.frame0 = t0;
+		a.n_frames = t1 - t0;
+		if ((rc = launch_stft(a, device, st)) != PAR_OK) return rc;
+		if ((rc = ss.after(ss.down, st)) != PAR_OK) return rc;
+		for (int c = 0; c < n_ch; c++) {
+			char *dst = (char *)out + ((size_t)c * out_ch_stride + (size_t)t0 * out_pitch) * esz;
+			const char *src = (const char *)dout.p + ((size_t)c * T * F + (size_t)t0 * F) * esz;
+			if (out_pitch == F) {
+				PAR_CUDA(cudaMemcpyAsync(dst, src, (size_t)(t1 - t0) * F * esz, cudaMemcpyDeviceToHost, ss.down));
+			} else {
+				PAR_CUDA(cudaMemcpy2DAsync(dst, out_pitch * esz, src, F * esz, F * esz, t1 - t0,
+				                           cudaMemcpyDeviceToHost, ss.down));
+			}
 		}
 	}
+	tm.stop();
+	if ((rc = ss.drain()) != PAR_OK) return rc;
 	PAR_CUDA(cudaStreamSynchronize(st));
 	tm.finish();
 	return PAR_OK;
@@ -418,7 +526,7 @@ PAR_API int par_istft_f32(const void *S, int n_fft, int64_t n_frames, int64_t s_
 	tm.start();
 	if ((rc = launch_istft(a, device, st)) != PAR_OK) return rc;
 	tm.stop();
-	if ((rc = download_out(dyo, y, length, y_stride, n_ch, y_ch_stride, st)) != PAR_OK) return rc;
+	if ((rc = download_out(dyo, y, 0, length, y_stride, n_ch, y_ch_stride, st)) != PAR_OK) return rc;
 	PAR_CUDA(cudaStreamSynchronize(st));
 	tm.finish();
 	return PAR_OK;
@@ -449,9 +557,14 @@ PAR_API int par_speed_segments(const double *sampletimes, const double *speeds, 
 // Speed curve -> device-resident read positions.  `pos` must hold `cap` doubles on the device;
 // *m_out receives the number of valid positions.  Synchronises `st` once (the per-segment sums
 // have to reach the host for the serial offset chain and the end test, util/resampling.py:125-135).
+struct SegChain {                 // host copy of the serial part of speed_to_pos
+	std::vector<int64_t> start;   // first output index of every segment
+	std::vector<double> off;      // carried offset = position just before the segment's first output
+};
+
 static int positions_device(const double *sampletimes, const double *speeds, int64_t k, double num_input_samples,
                             const std::vector<int64_t> &seg_n, int64_t total, double *pos, int64_t cap,
-                            int64_t *m_out, cudaStream_t st) {
+                            int64_t *m_out, cudaStream_t st, SegChain *chain = nullptr) {
 	int rc;
 	const int64_t n_seg = k - 1;
 	std::vector<int64_t> seg_start(n_seg);
@@ -512,6 +625,7 @@ static int positions_device(const double *sampletimes, const double *speeds, int
 		return PAR_ECAPACITY;
 	}
 	if (m == 0) return PAR_OK;
+	if (chain) { chain->start = seg_start; chain->off = off; }
 	PAR_CUDA(cudaMemcpyAsync(d_off.p, off.data(), n_seg * sizeof(double), cudaMemcpyHostToDevice, st));
 	rc = launch_expand_positions(d_sp.as<double>(), d_n.as<int64_t>(), d_start.as<int64_t>(), d_off.as<double>(),
 	                             n_seg, pos, m, st);
@@ -549,31 +663,70 @@ PAR_API int par_speed_to_pos_f64(const double *sampletimes, const double *speeds
 }
 
 // Resample with DEVICE positions; signal / out are host or device according to `flags`.
+// Host pointers: when the positions come from a speed curve with positive speeds (`chain`), they are
+// monotone and chunk boundaries are put on segment starts, where the host knows the read position:
+// chunks of the output then flow through upload -> interpolate -> download on three streams.
 static int resample_with_dev_pos(bool sinc, const double *dpos, int64_t m, const float *signal, int64_t n_in,
                                  int64_t sig_stride, int n_ch, int64_t sig_ch_stride, int nt,
                                  float *out, int64_t out_stride, int64_t out_ch_stride,
-                                 unsigned flags, int device, cudaStream_t st) {
+                                 unsigned flags, int device, cudaStream_t st, const SegChain *chain = nullptr,
+                                 bool monotone = false) {
 	int rc;
 	SincArgs a;
 	a.pos = dpos; a.m = m; a.n_in = n_in; a.n_ch = n_ch; a.nt = nt;
 	a.aligned_edges = (flags & PAR_SINC_ALIGNED_EDGES) ? 1 : 0;
+	a.out_begin = 0; a.out_end = m;
 	if (flags & PAR_DEVICE_PTRS) {
 		a.signal = signal; a.sig_stride = sig_stride; a.sig_ch_stride = sig_ch_stride;
 		a.out = out; a.out_stride = out_stride; a.out_ch_stride = out_ch_stride;
 		return sinc ? launch_sinc(a, device, st) : launch_linear(a, device, st);
 	}
-	DevBuf dsig(st), dout(st);
-	DevAudio da;
+	DevBuf dout(st);
+	AudioUploader up(st);
 	DevOut dd;
-	if ((rc = upload_audio(dsig, signal, n_in, sig_stride, n_ch, sig_ch_stride, st, &da)) != PAR_OK) return rc;
+	SideStreams ss;
+	if ((rc = up.init(signal, n_in, sig_stride, n_ch, sig_ch_stride)) != PAR_OK) return rc;
 	if ((rc = alloc_out(dout, m, out_stride, n_ch, out_ch_stride, st, &dd)) != PAR_OK) return rc;
+	if ((rc = ss.init()) != PAR_OK) return rc;
+	if ((rc = ss.after(ss.up, st)) != PAR_OK) return rc;
+	const DevAudio da = up.view();
 	a.signal = da.p; a.sig_stride = da.stride; a.sig_ch_stride = da.ch_stride;
 	a.out = dd.p; a.out_stride = dd.stride; a.out_ch_stride = dd.ch_stride;
 	EventTimer tm(st);
 	tm.start();
-	if ((rc = sinc ? launch_sinc(a, device, st) : launch_linear(a, device, st)) != PAR_OK) return rc;
+	int64_t per_chunk = chunk_bytes() / (int64_t)(sizeof(float) * n_ch);
+	if (per_chunk < 1024) per_chunk = 1024;
+	const bool pipelined = chain && monotone && m > 2 * per_chunk;
+	if (!pipelined) {
+		if ((rc = up.upload_to(n_in, ss.up)) != PAR_OK) return rc;
+		if ((rc = ss.after(st, ss.up)) != PAR_OK) return rc;
+		if ((rc = sinc ? launch_sinc(a, device, st) : launch_linear(a, device, st)) != PAR_OK) return rc;
+		if ((rc = ss.after(ss.down, st)) != PAR_OK) return rc;
+		if ((rc = download_out(dd, out, 0, m, out_stride, n_ch, out_ch_stride, ss.down)) != PAR_OK) return rc;
+	} else {
+		const int64_t n_seg = (int64_t)chain->start.size();
+		int64_t seg = 0, o0 = 0;
+		while (o0 < m) {
+			// advance to the first segment start at least per_chunk outputs ahead
+			while (seg < n_seg && chain->start[seg] < o0 + per_chunk) seg++;
+			int64_t o1 = m, need = n_in;
+			if (seg < n_seg && chain->start[seg] < m) {
+				o1 = chain->start[seg];
+				// outputs before segment `seg` read positions <= off[seg]; taps reach NT further
+				const double top = chain->off[seg] + (double)nt + 4.0;
+				need = top < (double)n_in ? (top > 0.0 ? (int64_t)top : 0) : n_in;
+			}
+			if ((rc = up.upload_to(need, ss.up)) != PAR_OK) return rc;
+			if ((rc = ss.after(st, ss.up)) != PAR_OK) return rc;
+			a.out_begin = o0; a.out_end = o1;
+			if ((rc = sinc ? launch_sinc(a, device, st) : launch_linear(a, device, st)) != PAR_OK) return rc;
+			if ((rc = ss.after(ss.down, st)) != PAR_OK) return rc;
+			if ((rc = download_out(dd, out, o0, o1, out_stride, n_ch, out_ch_stride, ss.down)) != PAR_OK) return rc;
+			o0 = o1;
+		}
+	}
 	tm.stop();
-	if ((rc = download_out(dd, out, m, out_stride, n_ch, out_ch_stride, st)) != PAR_OK) return rc;
+	if ((rc = ss.drain()) != PAR_OK) return rc;
 	PAR_CUDA(cudaStreamSynchronize(st));
 	tm.finish();
 	return PAR_OK;
@@ -641,9 +794,14 @@ PAR_API int par_varispeed_f32(const double *sampletimes, const double *speeds, i
 	std::vector<int64_t> seg_n(k - 1);
 	int64_t total = 0;
 	if ((rc = par_speed_segments(sampletimes, speeds, k, seg_n.data(), &total)) != PAR_OK) return rc;
+	// positive finite speeds and non-empty segments => monotone positions => pipelined host path
+	bool monotone = true;
+	for (int64_t i = 0; i < k; i++) monotone = monotone && speeds[i] > 0.0 && speeds[i] < 1e6;
+	for (int64_t i = 0; i + 1 < k; i++) monotone = monotone && seg_n[i] >= 2;
 	DevBuf dpos(st);
+	SegChain chain;
 	if ((rc = dpos.alloc((size_t)(total > 0 ? total : 1) * sizeof(double))) != PAR_OK) return rc;
-	rc = positions_device(sampletimes, speeds, k, (double)n_in, seg_n, total, dpos.as<double>(), total, m, st);
+	rc = positions_device(sampletimes, speeds, k, (double)n_in, seg_n, total, dpos.as<double>(), total, m, st, &chain);
 	if (rc != PAR_OK) return rc;
 	if (*m > out_cap) {
 		set_error("varispeed: output capacity too small (need *m samples per channel)");
@@ -651,7 +809,7 @@ PAR_API int par_varispeed_f32(const double *sampletimes, const double *speeds, i
 	}
 	if (*m == 0) return PAR_OK;
 	return resample_with_dev_pos(sinc, dpos.as<double>(), *m, signal, n_in, sig_stride, n_ch, sig_ch_stride, nt, out,
-	                             out_stride, out_ch_stride, flags, device, st);
+	                             out_stride, out_ch_stride, flags, device, st, &chain, monotone);
 }
 
 }  // extern "C"

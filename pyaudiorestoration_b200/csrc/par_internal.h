@@ -35,7 +35,8 @@ struct StftArgs {
 	const float *x;
 	int64_t n, x_stride, x_ch_stride;
 	int n_ch, n_fft, hop, zeropad;
-	int64_t n_frames;
+	int64_t n_frames;      // frames handled by this launch (per channel) ...
+	int64_t frame0;        // ... starting at this global frame index
 	const float *window;   // device
 	void *out;
 	int64_t out_pitch, out_ch_stride;
@@ -71,6 +72,7 @@ struct SincArgs {
 	float *out;
 	int64_t out_stride, out_ch_stride;
 	int aligned_edges;
+	int64_t out_begin, out_end;   // output range handled by this launch, [0, m) for all of it
 };
 int launch_sinc(const SincArgs &a, int device, cudaStream_t st);
 int launch_linear(const SincArgs &a, int device, cudaStream_t st);

@@ -344,7 +344,7 @@ sinc_kernel(SincArgs a, const float *__restrict__ ctab, const float *__restrict_
 	extern __shared__ __align__(16) float xs[];      // (span_cap + SINC_XPAD) samples x CH, channel-interleaved
 	__shared__ long long red_lo[SINC_TILE / 32], red_hi[SINC_TILE / 32];
 	const int nt = a.nt;
-	const int64_t tiles = (a.m + SINC_TILE - 1) / SINC_TILE;
+	const int64_t tiles = (a.out_end - a.out_begin + SINC_TILE - 1) / SINC_TILE;
 	const int groups = (a.n_ch + CH - 1) / CH;
 	const int64_t work = tiles * groups;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -353,8 +353,8 @@ sinc_kernel(SincArgs a, const float *__restrict__ ctab, const float *__restrict_
 		const int grp = (int)(wk / tiles);
 		const int64_t tile = wk - (int64_t)grp * tiles;
 		const int ch0 = grp * CH;
-		const int64_t i = tile * SINC_TILE + threadIdx.x;
-		const bool live = i < a.m;
+		const int64_t i = a.out_begin + tile * SINC_TILE + threadIdx.x;
+		const bool live = i < a.out_end;
 
 		SampleSetup su;
 		su.lower = 0; su.cnt = 0; su.koff = 0; su.s = 1e-30f; su.fc = 1.f; su.lowpass = false; su.f_fx = 0; su.s_fx = 0;
@@ -432,7 +432,7 @@ static int launch_sinc_ch(const SincArgs &a, int device, cudaStream_t st, const 
 	int occ = 0;
 	PAR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SINC_TILE, smem));
 	if (occ < 1) occ = 1;
-	const int64_t tiles = (a.m + SINC_TILE - 1) / SINC_TILE;
+	const int64_t tiles = (a.out_end - a.out_begin + SINC_TILE - 1) / SINC_TILE;
 	const int64_t work = tiles * ((a.n_ch + CH - 1) / CH);
 	int64_t grid = (int64_t)occ * sm_count(device);
 	if (grid > work) grid = work;
@@ -444,7 +444,7 @@ static int launch_sinc_ch(const SincArgs &a, int device, cudaStream_t st, const 
 }
 
 int launch_sinc(const SincArgs &a, int device, cudaStream_t st) {
-	if (a.m <= 0 || a.n_ch <= 0) return PAR_OK;
+	if (a.m <= 0 || a.n_ch <= 0 || a.out_end <= a.out_begin) return PAR_OK;
 	SincTables tb;
 	int rc = sinc_tables(device, a.nt, st, &tb);
 	if (rc != PAR_OK) return rc;
@@ -458,10 +458,11 @@ int launch_sinc(const SincArgs &a, int device, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 linear_kernel(SincArgs a) {
-	const int64_t total = a.m * a.n_ch;
+	const int64_t span = a.out_end - a.out_begin;
+	const int64_t total = span * a.n_ch;
 	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
 	     t += (int64_t)gridDim.x * blockDim.x) {
-		const int64_t ch = t / a.m, i = t - ch * a.m;
+		const int64_t ch = t / span, i = a.out_begin + (t - ch * span);
 		const double p = a.pos[i];
 		const float *x = a.signal + ch * a.sig_ch_stride;
 		float y = 0.f;
@@ -481,7 +482,7 @@ linear_kernel(SincArgs a) {
 }
 
 int launch_linear(const SincArgs &a, int device, cudaStream_t st) {
-	const int64_t total = a.m * a.n_ch;
+	const int64_t total = (a.out_end - a.out_begin) * a.n_ch;
 	if (total <= 0) return PAR_OK;
 	int64_t grid = (total + 255) / 256;
 	const int64_t cap = (int64_t)sm_count(device) * 16;

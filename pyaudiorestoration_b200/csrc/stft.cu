@@ -98,7 +98,7 @@ stft_kernel(StftArgs a, const float2 *__restrict__ tw, float half_scale) {
 		const int64_t f = g * C::FPB + slot;
 		const bool valid = f < total;
 		const int64_t ch = valid ? f / a.n_frames : 0;
-		const int64_t t = valid ? f - ch * a.n_frames : 0;
+		const int64_t t = a.frame0 + (valid ? f - ch * a.n_frames : 0);
 		FrameLoad ld;
 		ld.x = a.x + ch * a.x_ch_stride;
 		ld.n = a.n;

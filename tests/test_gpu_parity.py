@@ -474,3 +474,25 @@ def test_varispeed_capacity_error(par):
     rc = L.par_varispeed_f32(st.ctypes.data, sp.ctypes.data, 2, x.ctypes.data, 8000, 1, 1, 0, 1, 50,
                              out.ctypes.data, 100, 1, 0, m.ctypes.data, 0, _lib.device(), None)
     assert rc == _lib.PAR_ECAPACITY and m[0] == len(oracle.speed_to_pos_c(st, sp, 8000))
+
+
+def test_host_pipeline_chunking_is_invisible(fourier, resampling, monkeypatch):
+    """Host-pointer calls stream chunks through upload / kernel / download streams; results must
+    not depend on the chunk size (PAR_B200_CHUNK_BYTES forces many small chunks)."""
+    sr = 96000
+    sig = np.stack([synth(sr * 4, 61), synth(sr * 4, 62)], axis=1)
+    curve = wow_curve(4.0, sr, 1024, depth=0.05, freq=0.9)
+    ref_s = fourier.stft(sig[:, 1], 1024, 256)
+    ref_m = fourier.stft_multi(sig, 4096, 1024, magnitude=True)
+    ref_v = resampling.varispeed(sig, sr, curve, None, "Sinc", 50).copy()
+    ref_l = resampling.varispeed(sig[:, 0], sr, curve, None, "Linear").copy()
+    ref_s, ref_m = ref_s.copy(), ref_m.copy()
+    for chunk in ("4096", "70000", "1000000"):
+        monkeypatch.setenv("PAR_B200_CHUNK_BYTES", chunk)
+        assert np.array_equal(fourier.stft(sig[:, 1], 1024, 256), ref_s)
+        assert np.array_equal(fourier.stft_multi(sig, 4096, 1024, magnitude=True), ref_m)
+        assert np.array_equal(resampling.varispeed(sig, sr, curve, None, "Sinc", 50), ref_v)
+        assert np.array_equal(resampling.varispeed(sig[:, 0], sr, curve, None, "Linear"), ref_l)
+    monkeypatch.delenv("PAR_B200_CHUNK_BYTES")
+    pos = oracle.speed_to_pos_c(curve[:, 0] * sr, curve[:, 1], len(sig))
+    _check_sinc(np.ascontiguousarray(ref_v[:, 1]), pos, np.ascontiguousarray(sig[:, 1]), 50)
