@@ -228,6 +228,65 @@ struct SmemLoad {
 	__device__ __forceinline__ float2 operator()(int n) const { return src[pad16(n)]; }
 };
 
+// Sub-block ("slot") barrier: the TPF threads that share one transform synchronise among
+// themselves only (named barrier `id`, or a warp barrier when a transform fits one warp), so several
+// transforms in a CTA progress independently.
+template <int TPF>
+struct SlotSync {
+	int id;
+	__device__ __forceinline__ void operator()() const {
+		if (TPF <= 32) __syncwarp();
+		else asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(TPF) : "memory");
+	}
+};
+
+// In-place Stockham pass with the twiddle table in SHARED memory and a slot barrier.
+template <int LOG2M, int PASS, bool INV, class Load, class Sync>
+__device__ __forceinline__ void stockham_pass_slot(int tid, Load load, float2 *buf, const float2 *tw_s, Sync sync) {
+	using S = FftSched<LOG2M>;
+	constexpr int RB = S::bits(PASS);
+	constexpr int R = 1 << RB;
+	constexpr int NSL = S::ns_log2(PASS);
+	constexpr int NS = 1 << NSL;
+	constexpr int NB = S::P / R;
+	constexpr int STRIDE = S::M / R;
+	float2 v[NB][R];
+#pragma unroll
+	for (int b = 0; b < NB; b++) {
+		const int j = tid + b * S::TPF;
+#pragma unroll
+		for (int t = 0; t < R; t++) v[b][t] = load(j + t * STRIDE);
+	}
+	sync();
+#pragma unroll
+	for (int b = 0; b < NB; b++) {
+		const int j = tid + b * S::TPF;
+		const int k = j & (NS - 1);
+		if (PASS > 0) {
+			const float2 *twp = tw_s + S::tw_offset(PASS) + k;
+#pragma unroll
+			for (int t = 1; t < R; t++) v[b][t] = ctw<INV>(v[b][t], twp[(t - 1) * NS]);
+		}
+		Dft<R, INV>::run(v[b]);
+		const int j0 = ((j >> NSL) << (NSL + RB)) + k;
+#pragma unroll
+		for (int t = 0; t < R; t++) buf[pad16(j0 + t * NS)] = v[b][t];
+	}
+}
+
+template <int LOG2M, bool INV, int PASS, class Sync>
+struct RunPassesSlot {
+	__device__ __forceinline__ static void run(int tid, float2 *buf, const float2 *tw_s, Sync sync) {
+		using S = FftSched<LOG2M>;
+		if constexpr (PASS < S::NP) {
+			sync();   // stores of the previous pass -> loads of this one
+			stockham_pass_slot<LOG2M, PASS, INV>(tid, SmemLoad{buf}, buf, tw_s, sync);
+			RunPassesSlot<LOG2M, INV, PASS + 1, Sync>::run(tid, buf, tw_s, sync);
+		}
+	}
+};
+
+
 // Runs passes FIRST..NP-1 of a transform whose pass-(FIRST-1) output (or input, FIRST == 0)
 // sits in `cur`; ping-pongs between cur and alt (or works in place).  Returns the buffer that
 // holds the natural-order result.  Ends WITHOUT a trailing barrier after the last pass's stores.

@@ -392,10 +392,11 @@ sinc_kernel(SincArgs a, const float *__restrict__ ctab, const float *__restrict_
 		float acc[CH];
 #pragma unroll
 		for (int c = 0; c < CH; c++) acc[c] = 0.f;
+		// per-sample choice (not per warp): the result of a sample must not depend on which other
+		// samples share its warp, i.e. on how a host-pointer call was cut into chunks
 		const bool interior = su.cnt == 2 * nt && su.koff == 0;
-		const bool warp_fast = staged && __all_sync(0xffffffffu, interior || !live || su.cnt == 0);
 		if (live && su.cnt > 0) {
-			if (warp_fast) {
+			if (staged && interior) {
 				const float *xrow = xs + (int)(su.lower - tlo) * CH;
 				if (su.lowpass) taps_fast<CH, true>(su, nt, nblk, hptab, xrow, acc);
 				else taps_fast<CH, false>(su, nt, nblk, ctab, xrow, acc);
