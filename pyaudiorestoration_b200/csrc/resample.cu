@@ -128,6 +128,9 @@ int launch_expand_positions(const double *speeds_dev, const int64_t *seg_n_dev,
 // ------------------------------------------------------------------------------------------
 
 constexpr int SINC_TILE = 256;       // outputs per block iteration == threads per block
+#ifndef SINC_MIN_BLOCKS
+#define SINC_MIN_BLOCKS 3
+#endif
 constexpr int SINC_XPAD = 32;        // zero padding behind the staged span (the last tap block may overhang)
 
 __device__ __forceinline__ float rcp_approx(float x) {
@@ -234,19 +237,17 @@ struct RotTable {
 //   fc == 1: w = c[widx] / (d - s)                      (sinpi(s) is applied once at the end)
 //   fc <  1: w = hp[widx] * sin(theta_b + j*pi*fc) / (d - s), theta_b exact per block
 template <int CH, bool LOWPASS, bool DESC>
-__device__ __forceinline__ void tap_block(const SampleSetup &su, int b, int nt, const float *__restrict__ tab,
-                                          const RotTable &rot, float centre_sn, const float *xrow,
+__device__ __forceinline__ void tap_block(const SampleSetup &su, int b, int nt, const float *tab_s,
+                                          const RotTable &rot, float sa, float ca, float centre_sn, const float *xrow,
                                           float (&acc)[CH]) {
 	const int d0 = 16 * b - nt;
 	const bool near = d0 < 16 && d0 > -31;       // block holds a tap with |d| < 16
-	float sa = 0.f, ca = 0.f;
-	if (LOWPASS) sincos_fx(su.f_fx * (uint64_t)(int64_t)d0 - (uint64_t)su.s_fx, &sa, &ca);
 	const float base = (float)d0 - su.s;         // far blocks: |q| >= 15.5, one rounding is harmless
-	const float4 *t4 = reinterpret_cast<const float4 *>(tab + 16 * b);
+	const float4 *t4 = reinterpret_cast<const float4 *>(tab_s + 16 * b);
 #pragma unroll
 	for (int h = 0; h < 2; h++) {
 		const int hh = DESC ? 1 - h : h;
-		const float4 ta = __ldg(t4 + 2 * hh), tb = __ldg(t4 + 2 * hh + 1);
+		const float4 ta = t4[2 * hh], tb = t4[2 * hh + 1];
 		const float coef[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
 		float w[8];
 #pragma unroll
@@ -292,23 +293,42 @@ __device__ __forceinline__ void tap_block(const SampleSetup &su, int b, int nt, 
 // run is accumulated from its far end towards the centre (small terms first) in its own
 // accumulator; a plain left-to-right float32 sum costs ~1e-6 relative at NT >= 128.
 template <int CH, bool LOWPASS>
-__device__ __forceinline__ void taps_fast(const SampleSetup &su, int nt, int nblk, const float *__restrict__ tab,
+__device__ __forceinline__ void taps_fast(const SampleSetup &su, int nt, int nblk, const float *tab_s,
                                           const float *xrow, float (&out)[CH]) {
 	RotTable rot;
-	float centre_sn = 0.f;
+	float centre_sn = 0.f, s16 = 0.f, c16 = 1.f;
 	if (LOWPASS) {
 		rot.build(su.f_fx);
+		sincos_fx(su.f_fx * 16ull, &s16, &c16);
 		centre_sn = sinpif(su.fc * (0.f - su.s));     // numerator of the d = 0 tap, q = -s
 	}
 	float accl[CH], accr[CH];
 #pragma unroll
 	for (int c = 0; c < CH; c++) accl[c] = accr[c] = 0.f;
 	const int half = nblk >> 1;
+	// Block anchors sin/cos(pi fc (d0 - s)): exact from the fixed-point phase at the far end of each
+	// side and at every 4th block counted from the centre (always the block next to the centre);
+	// in between, one rotation by 16*pi*fc per block (error <= ~1e-7 per step, at |d| >= 16 only).
+	float sal = 0.f, cal = 1.f, sar = 0.f, car = 1.f;
 	for (int it = 0; it < half; it++) {
-		tap_block<CH, LOWPASS, false>(su, it, nt, tab, rot, centre_sn, xrow, accl);
-		tap_block<CH, LOWPASS, true>(su, nblk - 1 - it, nt, tab, rot, centre_sn, xrow, accr);
+		const int bl = it, br = nblk - 1 - it;
+		if (LOWPASS) {
+			if (it == 0 || ((half - 1 - it) & 3) == 0) {
+				sincos_fx(su.f_fx * (uint64_t)(int64_t)(16 * bl - nt) - (uint64_t)su.s_fx, &sal, &cal);
+				sincos_fx(su.f_fx * (uint64_t)(int64_t)(16 * br - nt) - (uint64_t)su.s_fx, &sar, &car);
+			} else {
+				const float nsl = fmaf(sal, c16, cal * s16), ncl = fmaf(cal, c16, -sal * s16);
+				const float nsr = fmaf(sar, c16, -car * s16), ncr = fmaf(car, c16, sar * s16);
+				sal = nsl; cal = ncl; sar = nsr; car = ncr;
+			}
+		}
+		tap_block<CH, LOWPASS, false>(su, bl, nt, tab_s, rot, sal, cal, centre_sn, xrow, accl);
+		tap_block<CH, LOWPASS, true>(su, br, nt, tab_s, rot, sar, car, centre_sn, xrow, accr);
 	}
-	if (nblk & 1) tap_block<CH, LOWPASS, false>(su, half, nt, tab, rot, centre_sn, xrow, accl);
+	if (nblk & 1) {
+		if (LOWPASS) sincos_fx(su.f_fx * (uint64_t)(int64_t)(16 * half - nt) - (uint64_t)su.s_fx, &sal, &cal);
+		tap_block<CH, LOWPASS, false>(su, half, nt, tab_s, rot, sal, cal, centre_sn, xrow, accl);
+	}
 #pragma unroll
 	for (int c = 0; c < CH; c++) out[c] = accl[c] + accr[c];
 }
@@ -339,11 +359,20 @@ __device__ __forceinline__ float taps_slow(const SampleSetup &su, int nt, const 
 }
 
 template <int CH>
-__global__ void __launch_bounds__(SINC_TILE, 2)
+__global__ void __launch_bounds__(SINC_TILE, SINC_MIN_BLOCKS)
 sinc_kernel(SincArgs a, const float *__restrict__ ctab, const float *__restrict__ hptab, int nblk, int span_cap) {
-	extern __shared__ __align__(16) float xs[];      // (span_cap + SINC_XPAD) samples x CH, channel-interleaved
+	extern __shared__ __align__(16) float smem_f[];
+	// [c table | hp table] (16 * (nblk + 1) floats each), then the staged samples:
+	// (span_cap + SINC_XPAD) samples x CH, channel-interleaved
+	float *ctab_s = smem_f;
+	float *hptab_s = smem_f + 16 * (nblk + 1);
+	float *xs = smem_f + 32 * (nblk + 1);
 	__shared__ long long red_lo[SINC_TILE / 32], red_hi[SINC_TILE / 32];
 	const int nt = a.nt;
+	for (int i = threadIdx.x; i < 16 * (nblk + 1); i += SINC_TILE) {
+		ctab_s[i] = __ldg(ctab + i);
+		hptab_s[i] = __ldg(hptab + i);
+	}
 	const int64_t tiles = (a.out_end - a.out_begin + SINC_TILE - 1) / SINC_TILE;
 	const int groups = (a.n_ch + CH - 1) / CH;
 	const int64_t work = tiles * groups;
@@ -398,8 +427,8 @@ sinc_kernel(SincArgs a, const float *__restrict__ ctab, const float *__restrict_
 		if (live && su.cnt > 0) {
 			if (staged && interior) {
 				const float *xrow = xs + (int)(su.lower - tlo) * CH;
-				if (su.lowpass) taps_fast<CH, true>(su, nt, nblk, hptab, xrow, acc);
-				else taps_fast<CH, false>(su, nt, nblk, ctab, xrow, acc);
+				if (su.lowpass) taps_fast<CH, true>(su, nt, nblk, hptab_s, xrow, acc);
+				else taps_fast<CH, false>(su, nt, nblk, ctab_s, xrow, acc);
 			} else {
 				// first / last NT outputs of a file, or a span too wide for shared memory
 #pragma unroll
@@ -427,7 +456,7 @@ template <int CH>
 static int launch_sinc_ch(const SincArgs &a, int device, cudaStream_t st, const SincTables &tb) {
 	// widest span staged in shared memory: a tile read at up to 4x speed
 	const int span_cap = 4 * SINC_TILE + 2 * a.nt;
-	const int smem = CH * (span_cap + SINC_XPAD) * (int)sizeof(float);
+	const int smem = (CH * (span_cap + SINC_XPAD) + 2 * tb.padded) * (int)sizeof(float);
 	auto kern = sinc_kernel<CH>;
 	PAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 	int occ = 0;

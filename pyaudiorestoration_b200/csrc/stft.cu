@@ -179,23 +179,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 	    : "memory");
 }
 
+template <bool FULL>     // FULL: zeropad == 1, every packed element carries samples
 struct StagedLoad {
 	const float2 *raw2;    // staged raw samples of this slot, as float2 pairs (shared memory)
 	const float2 *win2;    // window (shared memory)
 	int half_n;
 	__device__ __forceinline__ float2 operator()(int e) const {
-		if (e >= half_n) return make_float2(0.f, 0.f);
+		if (!FULL && e >= half_n) return make_float2(0.f, 0.f);
 		const float2 w = win2[e];
 		const float2 v = raw2[e];
 		return make_float2(v.x * w.x, v.y * w.y);
 	}
-};
-
-struct MixedLoad {
-	bool staged;
-	StagedLoad st;
-	FrameLoad fl;
-	__device__ __forceinline__ float2 operator()(int e) const { return staged ? st(e) : fl(e); }
 };
 
 // CTA = SLOTS independent transform slots of TPF threads each, sharing one shared-memory copy of the
@@ -271,31 +265,40 @@ stft_tma_kernel(StftArgs a, const float2 *__restrict__ tw, float half_scale) {
 			mbar_wait(bar, parity);
 			parity ^= 1;
 		}
-		MixedLoad ld;
-		ld.staged = staged;
-		ld.st = StagedLoad{reinterpret_cast<const float2 *>(stage), reinterpret_cast<const float2 *>(win_s), half_n};
-		ld.fl.x = a.x + ch * a.x_ch_stride;
-		ld.fl.n = a.n;
-		ld.fl.stride = a.x_stride;
-		ld.fl.base = t * a.hop - half_n;
-		ld.fl.win2 = reinterpret_cast<const float2 *>(a.window);
-		ld.fl.half_n = half_n;
-		ld.fl.valid = true;
-		ld.fl.fast = false;
 		// pass 0: its slot barrier sits between the loads (staging buffer, and the previous frame's
-		// epilogue reads of `buf`) and the stores into `buf`
-		stockham_pass_slot<LOG2M, 0, false>(tid, ld, buf, tw_s, sync);
+		// epilogue reads of `buf`) and the stores into `buf`.  `staged` is uniform over the slot.
+		if (staged) {
+			if (a.zeropad == 1) {
+				StagedLoad<true> ld{reinterpret_cast<const float2 *>(stage), reinterpret_cast<const float2 *>(win_s), half_n};
+				stockham_pass_slot<LOG2M, 0, false>(tid, ld, buf, tw_s, sync);
+			} else {
+				StagedLoad<false> ld{reinterpret_cast<const float2 *>(stage), reinterpret_cast<const float2 *>(win_s), half_n};
+				stockham_pass_slot<LOG2M, 0, false>(tid, ld, buf, tw_s, sync);
+			}
+		} else {
+			FrameLoad ld;
+			ld.x = a.x + ch * a.x_ch_stride;
+			ld.n = a.n;
+			ld.stride = a.x_stride;
+			ld.base = t * a.hop - half_n;
+			ld.win2 = reinterpret_cast<const float2 *>(a.window);
+			ld.half_n = half_n;
+			ld.valid = true;
+			ld.fast = false;
+			stockham_pass_slot<LOG2M, 0, false>(tid, ld, buf, tw_s, sync);
+		}
 		// every thread of the slot has consumed its staged samples: prefetch the next frame
 		if (tid == 0) issue(f + stride_f);
 		RunPassesSlot<LOG2M, false, 1, SlotSync<S::TPF>>::run(tid, buf, tw_s, sync);
 		sync();
 
 		const int64_t row = ch * a.out_ch_stride + t * a.out_pitch;
-		for (int k = tid; k <= S::M / 2; k += S::TPF) {
+		// bins k and M-k come from z[k], z[M-k]: 2E = zk + conj(zm); 2O = -i (zk - conj(zm));
+		// X[k] = E + W^k O; X[M-k] = conj(E - W^k O).  k = 0 pairs with itself (bins 0 and M).
+		auto split_store = [&](int k, bool both) {
 			const float2 zk = buf[pad16(k)];
 			const float2 zm = buf[pad16((S::M - k) & (S::M - 1))];
 			const float2 w = tws[k];
-			// 2E = zk + conj(zm); 2O = -i (zk - conj(zm)); X[k] = E + W^k O; X[M-k] = conj(E - W^k O)
 			const float ex = zk.x + zm.x, ey = zk.y - zm.y;
 			const float ox = zk.y + zm.y, oy = zm.x - zk.x;
 			const float2 wo = cmul(make_float2(ox, oy), w);
@@ -304,12 +307,19 @@ stft_tma_kernel(StftArgs a, const float2 *__restrict__ tw, float half_scale) {
 			if (MAG) {
 				float *o = reinterpret_cast<float *>(a.out) + row;
 				o[k] = sqrtf(fmaf(xa.x, xa.x, xa.y * xa.y)) + 1e-7f;
-				if (k != S::M - k) o[S::M - k] = sqrtf(fmaf(xb.x, xb.x, xb.y * xb.y)) + 1e-7f;
+				if (both) o[S::M - k] = sqrtf(fmaf(xb.x, xb.x, xb.y * xb.y)) + 1e-7f;
 			} else {
 				float2 *o = reinterpret_cast<float2 *>(a.out) + row;
 				o[k] = xa;
-				if (k != S::M - k) o[S::M - k] = xb;
+				if (both) o[S::M - k] = xb;
 			}
+		};
+		if constexpr ((S::M / 2) % S::TPF == 0) {
+#pragma unroll
+			for (int i = 0; i < (S::M / 2) / S::TPF; i++) split_store(tid + i * S::TPF, true);
+			if (tid == 0) split_store(S::M / 2, false);
+		} else {
+			for (int k = tid; k <= S::M / 2; k += S::TPF) split_store(k, k != S::M - k);
 		}
 	}
 }
