@@ -204,6 +204,98 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------ GPU arm, time shards
+def run_time_sharded(args, torch, dist, rank, world, local, dev):
+    """ONE job (all channels of the workload) cut into `world` time chunks: per step
+    one broadcast of the speed curve, one all-gather of the chunks' edge samples, then every rank
+    transforms the frames and resamples the outputs that fall into its chunk.  Strong scaling."""
+    from pyaudiorestoration_b200 import _lib, dist as pdist
+    L = _lib.lib()
+    sr, dur, C, desc = WORKLOADS[args.workload]
+    n = int(sr * dur)
+    sh = pdist.TimeShard(n, N_FFT, HOP, NT, rank, world)
+    ln = sh.s1 - sh.s0
+    host_chunk = _lib.pinned_empty((C, ln), np.float32)
+    for c in range(C):
+        synth_channel(ln, sr, 1234 + c + 100 * rank, out=host_chunk[c])
+    buf = sh.local_buffer(C, dev)
+    sh.chunk_view(buf).copy_(torch.from_numpy(host_chunk))
+    curve = wow_curve(dur, sr) if rank == 0 else None
+    window = np.ascontiguousarray(__import__("scipy.signal").signal.get_window("blackmanharris", N_FFT), dtype=np.float32)
+    nfr, F = sh.frame1 - sh.frame0, N_FFT // 2 + 1
+    S_out = torch.empty((C, nfr, F), dtype=torch.complex64, device=dev)
+    pos_buf = torch.empty(int(ln * 1.1) + 8 * HOP, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step(upload=False):
+        if upload:                                   # e2e: this step's audio comes from (pinned) host memory
+            sh.chunk_view(buf).copy_(torch.from_numpy(host_chunk), non_blocking=True)
+        cv = pdist.broadcast_curve(curve, src=0, device=dev)
+        sh.exchange_halos(buf)
+        sh.stft(buf, window, out=S_out)
+        ps, p0, m = sh.positions(cv[:, 0] * sr, cv[:, 1], dev, out=pos_buf)
+        y = sh.resample(buf, ps, "Sinc", pos_origin=p0, m=m)
+        return y, m
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    launches0 = L.par_kernel_launch_count()
+    clocks = ClockSampler(local)
+    clocks.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record(stream)
+    for _ in range(args.steps):
+        y, m = step()
+    t1.record(stream)
+    barrier()
+    tm = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms = float(tm.item())
+    clk = clocks.stop()
+    launches = L.par_kernel_launch_count() - launches0
+    # e2e: host chunk in, spectrogram + resampled audio back in pinned host memory
+    S_host = torch.empty(S_out.shape, dtype=S_out.dtype).pin_memory()
+    y_host = torch.empty((C, int(ln * 1.1) + 8 * HOP), dtype=torch.float32).pin_memory()
+    e_steps = max(2, min(args.steps, 5))
+
+    def e2e_step():
+        y, m = step(upload=True)
+        S_host.copy_(S_out, non_blocking=True)
+        y_host[:, :y.shape[1]].copy_(y, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        return y.shape[1]
+    e2e_step()
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(e_steps):
+        mine = e2e_step()
+    dt = torch.tensor([time.perf_counter() - w0], dtype=torch.float64, device=dev)
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": n * C * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32 (positions f64)", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "sample_rate": sr, "seconds": dur, "channels": C,
+                       "samples_per_channel": n, "n_fft": N_FFT, "hop": HOP, "sinc_quality": NT,
+                       "parallelism": f"time chunks x{world}, halo {sh.H} samples, 1 all-gather of edge blocks + 1 curve "
+                                      f"broadcast per step",
+                       "l2": "per-rank inputs and outputs exceed the 126 MB L2; no flush"},
+            "e2e": {"value": n * C * e_steps / float(dt.item()), "unit": UNIT,
+                    "h2d_bytes_per_step": int(C * ln * 4), "d2h_bytes_per_step": int(C * nfr * F * 8 + C * mine * 4),
+                    "steps": e_steps, "ms_per_step": float(dt.item()) / e_steps * 1e3,
+                    "api": "per rank: pinned host chunk -> TimeShard.exchange_halos/stft/positions/resample -> pinned host"},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": None, "cpu_baseline": None,
+        }
+        print(json.dumps(line), flush=True)
+
+
 # ------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -212,6 +304,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--shard", default="channels", choices=["channels", "time"],
+                    help="N > 1: every rank its own channels (weak scaling, default) or one job cut into time chunks "
+                         "with a boundary all-gather (strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -237,6 +332,11 @@ def main():
     from pyaudiorestoration_b200.util import fourier, resampling
     L = _lib.lib()
     _lib.require_device()
+
+    if args.shard == "time" and world > 1:
+        run_time_sharded(args, torch, dist, rank, world, local, dev)
+        dist.destroy_process_group()
+        return
 
     sr, dur, ch_total, desc = WORKLOADS[args.workload]
     if args.workload == "cfg3":

@@ -143,6 +143,41 @@ PAR_API int par_varispeed_f32(const double *sampletimes, const double *speeds, i
                       int mode, int nt, float *out, int64_t out_cap, int64_t out_stride, int64_t out_ch_stride,
                       int64_t *m, unsigned flags, int device, void *stream);
 
+/* ---- time-sharded jobs: one rank's slice of a long signal --------------------
+ * Device pointers only (PAR_DEVICE_PTRS must be set).  Indices are GLOBAL sample / frame / output
+ * numbers; the rank passes the slice it holds and where that slice starts.
+ *
+ * par_stft_range_f32: frames [frame0, frame0 + n_frames) of the transform of a signal of n_global
+ * samples.  x holds samples [x_origin, x_origin + n_local) of every channel (planar, unit stride,
+ * channel c at + c * x_ch_stride), which must cover [frame0*hop - n_fft/2, (frame0+n_frames-1)*hop +
+ * n_fft/2) -- i.e. the rank's chunk plus a halo of up to n_fft/2 samples from each neighbour;
+ * reflection (util/fourier.py:80) happens only at 0 and n_global.  Row 0 of out is frame frame0. */
+PAR_API int par_stft_range_f32(const float *x, int64_t n_local, int64_t x_origin, int64_t n_global, int n_ch,
+                       int64_t x_ch_stride, int n_fft, int hop, int zeropad, const float *window,
+                       int64_t frame0, int64_t n_frames, void *out, int64_t out_pitch, int64_t out_ch_stride,
+                       unsigned flags, int device, void *stream);
+
+/* par_speed_to_pos_range_f64: the slice of util/resampling.py:93-137's positions a time shard needs.
+ * The serial segment chain is evaluated for the whole curve (it is K additions), but only the
+ * segments holding positions in [lo_pos, hi_pos] -- plus the following one, for the period of the
+ * last output -- are expanded.  pos[0] is output *pos_origin, *pos_count positions are written
+ * (bit-identical to the same slice of par_speed_to_pos_f64), *m is the global output count. */
+PAR_API int par_speed_to_pos_range_f64(const double *sampletimes, const double *speeds, int64_t k,
+                               double num_input_samples, double lo_pos, double hi_pos,
+                               double *pos, int64_t cap, int64_t *pos_origin, int64_t *pos_count,
+                               int64_t *m, unsigned flags, int device, void *stream);
+
+/* par_resample_range_f32: outputs [out_begin, out_end) of util/resampling.py:51-90 / :228-229 over
+ * m_global read positions.  pos holds positions [pos_origin, pos_origin + pos_count) and must reach
+ * out_end (the period of the last output) unless out_end == m_global; signal holds samples
+ * [sig_origin, sig_origin + sig_count) of every channel (planar) and must cover every tap the
+ * outputs read (round(pos) +- nt, clamped to [0, n_in_global)).  out[0] is output out_begin. */
+PAR_API int par_resample_range_f32(const double *pos, int64_t pos_origin, int64_t pos_count, int64_t m_global,
+                           int64_t out_begin, int64_t out_end, const float *signal, int64_t sig_origin,
+                           int64_t sig_count, int64_t n_in_global, int n_ch, int64_t sig_ch_stride, int mode, int nt,
+                           float *out, int64_t out_stride, int64_t out_ch_stride,
+                           unsigned flags, int device, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,7 +24,7 @@ EXPORTS = (
     "par_last_error", "par_version", "par_device_count", "par_kernel_launch_count",
     "par_last_kernel_ms", "par_host_alloc", "par_host_free", "par_stft_num_frames", "par_stft_f32",
     "par_istft_f32", "par_speed_segments", "par_speed_to_pos_f64", "par_sinc_resample_f32",
-    "par_linear_resample_f32", "par_varispeed_f32",
+    "par_linear_resample_f32", "par_varispeed_f32", "par_stft_range_f32", "par_resample_range_f32", "par_speed_to_pos_range_f64",
 )
 
 
@@ -65,6 +65,13 @@ def _declare(L):
     L.par_sinc_resample_f32.argtypes = [vp, i64, vp, i64, i64, i32, i64, i32, vp, i64, i64, u32, i32, vp]
     L.par_linear_resample_f32.restype = i32
     L.par_linear_resample_f32.argtypes = [vp, i64, vp, i64, i64, i32, i64, vp, i64, i64, u32, i32, vp]
+    L.par_stft_range_f32.restype = i32
+    L.par_stft_range_f32.argtypes = [vp, i64, i64, i64, i32, i64, i32, i32, i32, vp, i64, i64, vp, i64, i64, u32, i32, vp]
+    L.par_resample_range_f32.restype = i32
+    L.par_resample_range_f32.argtypes = [vp, i64, i64, i64, i64, i64, vp, i64, i64, i64, i32, i64, i32, i32, vp, i64,
+                                         i64, u32, i32, vp]
+    L.par_speed_to_pos_range_f64.restype = i32
+    L.par_speed_to_pos_range_f64.argtypes = [vp, vp, i64, dbl, dbl, dbl, vp, i64, vp, vp, vp, u32, i32, vp]
     L.par_varispeed_f32.restype = i32
     L.par_varispeed_f32.argtypes = [vp, vp, i64, vp, i64, i64, i32, i64, i32, i32, vp, i64, i64, i64, vp, u32,
                                     i32, vp]

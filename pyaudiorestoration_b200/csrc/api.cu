@@ -421,7 +421,7 @@ PAR_API int par_stft_f32(const float *x, int64_t n, int64_t x_stride, int n_ch, 
 	const bool mag = flags & PAR_OUT_MAGNITUDE;
 	StftArgs a;
 	a.n = n; a.n_ch = n_ch; a.n_fft = n_fft; a.hop = hop; a.zeropad = zeropad; a.n_frames = T;
-	a.window = dwin; a.magnitude = mag ? 1 : 0; a.frame0 = 0;
+	a.window = dwin; a.magnitude = mag ? 1 : 0; a.frame0 = 0; a.x_origin = 0;
 	if (flags & PAR_DEVICE_PTRS) {
 		a.x = x; a.x_stride = x_stride; a.x_ch_stride = x_ch_stride;
 		a.out = out; a.out_pitch = out_pitch; a.out_ch_stride = out_ch_stride;
@@ -564,7 +564,11 @@ struct SegChain {                 // host copy of the serial part of speed_to_po
 
 static int positions_device(const double *sampletimes, const double *speeds, int64_t k, double num_input_samples,
                             const std::vector<int64_t> &seg_n, int64_t total, double *pos, int64_t cap,
-                            int64_t *m_out, cudaStream_t st, SegChain *chain = nullptr) {
+                            int64_t *m_out, cudaStream_t st, SegChain *chain = nullptr,
+                            const double *window = nullptr, int64_t *win_origin = nullptr,
+                            int64_t *win_count = nullptr) {
+	// window = {lo, hi}: expand only the segments that hold positions in [lo, hi] (plus the segment
+	// after them, for the period of the last output); pos[0] is then output *win_origin
 	int rc;
 	const int64_t n_seg = k - 1;
 	std::vector<int64_t> seg_start(n_seg);
@@ -620,15 +624,32 @@ static int positions_device(const double *sampletimes, const double *speeds, int
 		offset = last;
 	}
 	*m_out = m;
-	if (m > cap) {
+	int64_t seg_a = 0, seg_b = n_seg;          // segments [seg_a, seg_b) are expanded
+	if (window) {
+		// off[i] = position just before segment i's first output; positions grow with i for positive speeds
+		while (seg_a + 1 < n_seg && off[seg_a + 1] < window[0]) seg_a++;
+		seg_b = seg_a;
+		while (seg_b < n_seg && off[seg_b] <= window[1]) seg_b++;
+		if (seg_b < n_seg) seg_b++;
+		const int64_t o_begin = seg_start[seg_a] < m ? seg_start[seg_a] : m;
+		const int64_t o_end = seg_b < n_seg ? (seg_start[seg_b] < m ? seg_start[seg_b] : m) : m;
+		*win_origin = o_begin;
+		*win_count = o_end - o_begin;
+		if (*win_count > cap) {
+			set_error("speed_to_pos: output capacity too small");
+			return PAR_ECAPACITY;
+		}
+		if (*win_count <= 0) return PAR_OK;
+		pos -= o_begin;                          // the kernel indexes globally
+	} else if (m > cap) {
 		set_error("speed_to_pos: output capacity too small");
 		return PAR_ECAPACITY;
 	}
 	if (m == 0) return PAR_OK;
 	if (chain) { chain->start = seg_start; chain->off = off; }
 	PAR_CUDA(cudaMemcpyAsync(d_off.p, off.data(), n_seg * sizeof(double), cudaMemcpyHostToDevice, st));
-	rc = launch_expand_positions(d_sp.as<double>(), d_n.as<int64_t>(), d_start.as<int64_t>(), d_off.as<double>(),
-	                             n_seg, pos, m, st);
+	rc = launch_expand_positions(d_sp.as<double>() + seg_a, d_n.as<int64_t>() + seg_a, d_start.as<int64_t>() + seg_a,
+	                             d_off.as<double>() + seg_a, seg_b - seg_a, pos, m, st);
 	if (rc != PAR_OK) return rc;
 	// `off` (pageable) must outlive its async copy
 	PAR_CUDA(cudaStreamSynchronize(st));
@@ -662,6 +683,25 @@ PAR_API int par_speed_to_pos_f64(const double *sampletimes, const double *speeds
 	return PAR_OK;
 }
 
+extern "C" PAR_API int par_speed_to_pos_range_f64(const double *sampletimes, const double *speeds, int64_t k,
+                                                  double num_input_samples, double lo_pos, double hi_pos,
+                                                  double *pos, int64_t cap, int64_t *pos_origin, int64_t *pos_count,
+                                                  int64_t *m, unsigned flags, int device, void *stream) {
+	if (!(flags & PAR_DEVICE_PTRS)) { set_error("speed_to_pos_range: device pointers only"); return PAR_EUNSUPPORTED; }
+	if (!sampletimes || !speeds || k < 2 || !m || !pos_origin || !pos_count || !pos || !(lo_pos <= hi_pos)) {
+		set_error("speed_to_pos_range: bad argument");
+		return PAR_EINVAL;
+	}
+	int rc = use_device(device);
+	if (rc != PAR_OK) return rc;
+	std::vector<int64_t> seg_n(k - 1);
+	int64_t total = 0;
+	if ((rc = par_speed_segments(sampletimes, speeds, k, seg_n.data(), &total)) != PAR_OK) return rc;
+	const double window[2] = {lo_pos, hi_pos};
+	return positions_device(sampletimes, speeds, k, num_input_samples, seg_n, total, pos, cap, m, (cudaStream_t)stream,
+	                        nullptr, window, pos_origin, pos_count);
+}
+
 // Resample with DEVICE positions; signal / out are host or device according to `flags`.
 // Host pointers: when the positions come from a speed curve with positive speeds (`chain`), they are
 // monotone and chunk boundaries are put on segment starts, where the host knows the read position:
@@ -676,6 +716,7 @@ static int resample_with_dev_pos(bool sinc, const double *dpos, int64_t m, const
 	a.pos = dpos; a.m = m; a.n_in = n_in; a.n_ch = n_ch; a.nt = nt;
 	a.aligned_edges = (flags & PAR_SINC_ALIGNED_EDGES) ? 1 : 0;
 	a.out_begin = 0; a.out_end = m;
+	a.pos_origin = a.sig_origin = a.out_origin = 0;
 	if (flags & PAR_DEVICE_PTRS) {
 		a.signal = signal; a.sig_stride = sig_stride; a.sig_ch_stride = sig_ch_stride;
 		a.out = out; a.out_stride = out_stride; a.out_ch_stride = out_ch_stride;
@@ -810,6 +851,79 @@ PAR_API int par_varispeed_f32(const double *sampletimes, const double *speeds, i
 	if (*m == 0) return PAR_OK;
 	return resample_with_dev_pos(sinc, dpos.as<double>(), *m, signal, n_in, sig_stride, n_ch, sig_ch_stride, nt, out,
 	                             out_stride, out_ch_stride, flags, device, st, &chain, monotone);
+}
+
+// ---- shard entry points (device pointers only): one rank's slice of a time-sharded job ----------
+PAR_API int par_stft_range_f32(const float *x, int64_t n_local, int64_t x_origin, int64_t n_global, int n_ch,
+                       int64_t x_ch_stride, int n_fft, int hop, int zeropad, const float *window,
+                       int64_t frame0, int64_t n_frames, void *out, int64_t out_pitch, int64_t out_ch_stride,
+                       unsigned flags, int device, void *stream) {
+	if (!(flags & PAR_DEVICE_PTRS)) { set_error("stft_range: device pointers only"); return PAR_EUNSUPPORTED; }
+	if (!x || !out || !window) { set_error("stft_range: null pointer"); return PAR_EINVAL; }
+	const int64_t T = par_stft_num_frames(n_global, n_fft, hop);
+	const int64_t F = (int64_t)n_fft * zeropad / 2 + 1;
+	if (n_global < 1 || n_local < 1 || n_ch < 1 || n_fft < 2 || hop < 1 || zeropad < 1 || x_origin < 0 ||
+	    x_origin + n_local > n_global || frame0 < 0 || n_frames < 0 || frame0 + n_frames > T || out_pitch < F) {
+		set_error("stft_range: bad size argument");
+		return PAR_EINVAL;
+	}
+	if (n_frames == 0) return PAR_OK;
+	// the slice must hold every sample its frames read: [frame0*hop - n_fft/2, (frame0+n_frames-1)*hop + n_fft/2),
+	// reflected into [0, n_global) at the two ends of the signal
+	const int64_t half = n_fft / 2;
+	int64_t lo = frame0 * hop - half, hi = (frame0 + n_frames - 1) * hop - half + n_fft;
+	if (lo < 0) { if (-lo + 1 > hi) hi = -lo + 1; lo = 0; }
+	if (hi > n_global) { const int64_t r = 2 * (n_global - 1) - (hi - 1); if (r < lo) lo = r < 0 ? 0 : r; hi = n_global; }
+	if (lo < x_origin || hi > x_origin + n_local) {
+		set_error("stft_range: the slice does not cover the samples (with halo) its frames read");
+		return PAR_EINVAL;
+	}
+	int rc = use_device(device);
+	if (rc != PAR_OK) return rc;
+	cudaStream_t st = (cudaStream_t)stream;
+	const float *dwin = device_window(device, window, n_fft, st);
+	if (!dwin) return PAR_ECUDA;
+	StftArgs a;
+	a.x = x; a.n = n_global; a.x_stride = 1; a.x_ch_stride = x_ch_stride; a.x_origin = x_origin;
+	a.n_ch = n_ch; a.n_fft = n_fft; a.hop = hop; a.zeropad = zeropad;
+	a.n_frames = n_frames; a.frame0 = frame0; a.window = dwin; a.magnitude = (flags & PAR_OUT_MAGNITUDE) ? 1 : 0;
+	// row 0 of `out` is frame `frame0`
+	const size_t esz = a.magnitude ? sizeof(float) : sizeof(float2);
+	a.out = (char *)out - (size_t)frame0 * out_pitch * esz;
+	a.out_pitch = out_pitch; a.out_ch_stride = out_ch_stride;
+	return launch_stft(a, device, st);
+}
+
+PAR_API int par_resample_range_f32(const double *pos, int64_t pos_origin, int64_t pos_count, int64_t m_global,
+                           int64_t out_begin, int64_t out_end, const float *signal, int64_t sig_origin,
+                           int64_t sig_count, int64_t n_in_global, int n_ch, int64_t sig_ch_stride, int mode, int nt,
+                           float *out, int64_t out_stride, int64_t out_ch_stride,
+                           unsigned flags, int device, void *stream) {
+	if (!(flags & PAR_DEVICE_PTRS)) { set_error("resample_range: device pointers only"); return PAR_EUNSUPPORTED; }
+	const bool sinc = mode == PAR_MODE_SINC;
+	if ((mode != PAR_MODE_LINEAR && !sinc) || !pos || !signal || !out || n_ch < 1 || out_stride < 1 ||
+	    (sinc && (nt < 1 || nt > 512)) || out_begin < 0 || out_end < out_begin || out_end > m_global ||
+	    pos_origin > out_begin || pos_origin < 0 || sig_origin < 0 || sig_origin + sig_count > n_in_global) {
+		set_error("resample_range: bad argument");
+		return PAR_EINVAL;
+	}
+	// the positions slice must reach one past the last output (period of the last sample) unless that is the end
+	const int64_t need_pos_end = out_end < m_global ? out_end + 1 : m_global;
+	const int64_t need_pos_begin = (out_end == m_global && m_global >= 2 && out_begin > m_global - 2) ? m_global - 2 : out_begin;
+	if (pos_origin > need_pos_begin || pos_origin + pos_count < need_pos_end) {
+		set_error("resample_range: the positions slice does not cover [out_begin, out_end] (+1)");
+		return PAR_EINVAL;
+	}
+	if (out_end == out_begin) return PAR_OK;
+	int rc = use_device(device);
+	if (rc != PAR_OK) return rc;
+	SincArgs a;
+	a.pos = pos; a.m = m_global; a.signal = signal; a.n_in = n_in_global; a.sig_stride = 1; a.sig_ch_stride = sig_ch_stride;
+	a.n_ch = n_ch; a.nt = nt; a.out = out; a.out_stride = out_stride; a.out_ch_stride = out_ch_stride;
+	a.aligned_edges = (flags & PAR_SINC_ALIGNED_EDGES) ? 1 : 0;
+	a.out_begin = out_begin; a.out_end = out_end;
+	a.pos_origin = pos_origin; a.sig_origin = sig_origin; a.out_origin = out_begin;
+	return sinc ? launch_sinc(a, device, (cudaStream_t)stream) : launch_linear(a, device, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -32,8 +32,9 @@ int sinc_tables(int device, int nt, cudaStream_t st, SincTables *out);
 
 // ---- kernel launchers (all asynchronous on `st`, device pointers only) -----------------------
 struct StftArgs {
-	const float *x;
-	int64_t n, x_stride, x_ch_stride;
+	const float *x;        // sample `x_origin` of every channel (shards hold a slice of the signal)
+	int64_t n, x_stride, x_ch_stride;   // n = GLOBAL length (reflection happens at 0 and n)
+	int64_t x_origin;
 	int n_ch, n_fft, hop, zeropad;
 	int64_t n_frames;      // frames handled by this launch (per channel) ...
 	int64_t frame0;        // ... starting at this global frame index
@@ -73,6 +74,8 @@ struct SincArgs {
 	int64_t out_stride, out_ch_stride;
 	int aligned_edges;
 	int64_t out_begin, out_end;   // output range handled by this launch, [0, m) for all of it
+	// shards: pos[0] is position `pos_origin`, signal[0] is sample `sig_origin`, out[0] is output `out_origin`
+	int64_t pos_origin, sig_origin, out_origin;
 };
 int launch_sinc(const SincArgs &a, int device, cudaStream_t st);
 int launch_linear(const SincArgs &a, int device, cudaStream_t st);

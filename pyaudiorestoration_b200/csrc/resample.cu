@@ -179,10 +179,11 @@ struct SampleSetup {
 __device__ __forceinline__ SampleSetup sample_setup(const SincArgs &a, int64_t i) {
 	SampleSetup su;
 	const int nt = a.nt;
-	const double p = a.pos[i];
+	const double *pos = a.pos - a.pos_origin;
+	const double p = pos[i];
 	double per;
-	if (i + 1 < a.m) per = fmax(1e-12, a.pos[i + 1] - p);
-	else per = a.m >= 2 ? fmax(1e-12, a.pos[a.m - 1] - a.pos[a.m - 2]) : 0.0;
+	if (i + 1 < a.m) per = fmax(1e-12, pos[i + 1] - p);
+	else per = a.m >= 2 ? fmax(1e-12, pos[a.m - 1] - pos[a.m - 2]) : 0.0;
 	double fc = 1.0 / per;
 	if (!(fc < 1.0)) fc = 1.0;
 	double pr = rint(p);                        // half to even, like Python's round()
@@ -412,7 +413,7 @@ sinc_kernel(SincArgs a, const float *__restrict__ ctab, const float *__restrict_
 				const int e = idx / CH, c = idx - e * CH;
 				float v = 0.f;
 				if (e < valid && ch0 + c < a.n_ch)
-					v = __ldg(a.signal + (int64_t)(ch0 + c) * a.sig_ch_stride + (tlo + e) * a.sig_stride);
+					v = __ldg(a.signal + (int64_t)(ch0 + c) * a.sig_ch_stride + (tlo + e - a.sig_origin) * a.sig_stride);
 				xs[idx] = v;
 			}
 		}
@@ -434,7 +435,8 @@ sinc_kernel(SincArgs a, const float *__restrict__ ctab, const float *__restrict_
 #pragma unroll
 				for (int c = 0; c < CH; c++)
 					if (ch0 + c < a.n_ch)
-						acc[c] = taps_slow(su, nt, ctab, hptab, a.signal + (int64_t)(ch0 + c) * a.sig_ch_stride,
+						acc[c] = taps_slow(su, nt, ctab, hptab,
+						                   a.signal + (int64_t)(ch0 + c) * a.sig_ch_stride - a.sig_origin * a.sig_stride,
 						                   a.sig_stride);
 			}
 			if (!su.lowpass) {
@@ -446,7 +448,7 @@ sinc_kernel(SincArgs a, const float *__restrict__ ctab, const float *__restrict_
 		if (live) {
 #pragma unroll
 			for (int c = 0; c < CH; c++)
-				if (ch0 + c < a.n_ch) a.out[(int64_t)(ch0 + c) * a.out_ch_stride + i * a.out_stride] = acc[c];
+				if (ch0 + c < a.n_ch) a.out[(int64_t)(ch0 + c) * a.out_ch_stride + (i - a.out_origin) * a.out_stride] = acc[c];
 		}
 		__syncthreads();
 	}
@@ -493,8 +495,8 @@ linear_kernel(SincArgs a) {
 	for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
 	     t += (int64_t)gridDim.x * blockDim.x) {
 		const int64_t ch = t / span, i = a.out_begin + (t - ch * span);
-		const double p = a.pos[i];
-		const float *x = a.signal + ch * a.sig_ch_stride;
+		const double p = a.pos[i - a.pos_origin];
+		const float *x = a.signal + ch * a.sig_ch_stride - a.sig_origin * a.sig_stride;
 		float y = 0.f;
 		if (p >= 0.0 && p <= (double)(a.n_in - 1)) {
 			long long j = (long long)floor(p);
@@ -507,7 +509,7 @@ linear_kernel(SincArgs a) {
 				y = (float)__dadd_rn(__dmul_rn(__dsub_rn(f1, f0), __dsub_rn(p, (double)j)), f0);
 			}
 		}
-		a.out[ch * a.out_ch_stride + i * a.out_stride] = y;
+		a.out[ch * a.out_ch_stride + (i - a.out_origin) * a.out_stride] = y;
 	}
 }
 

@@ -26,8 +26,8 @@ __device__ __forceinline__ int64_t reflect_index(int64_t i, int64_t n) {
 }
 
 struct FrameLoad {
-	const float *x;        // channel base
-	int64_t n, stride, base;
+	const float *x;        // channel base = sample `origin`
+	int64_t n, stride, base, origin;
 	const float2 *win2;    // window as float2 pairs
 	int half_n;            // N/2: packed elements that carry samples
 	bool fast, valid;
@@ -37,12 +37,12 @@ struct FrameLoad {
 		const int64_t s = base + 2 * (int64_t)e;
 		float a, b;
 		if (fast) {
-			const float2 v = __ldg(reinterpret_cast<const float2 *>(x + s));
+			const float2 v = __ldg(reinterpret_cast<const float2 *>(x + (s - origin)));
 			a = v.x;
 			b = v.y;
 		} else {
-			a = __ldg(x + reflect_index(s, n) * stride);
-			b = __ldg(x + reflect_index(s + 1, n) * stride);
+			a = __ldg(x + (reflect_index(s, n) - origin) * stride);
+			b = __ldg(x + (reflect_index(s + 1, n) - origin) * stride);
 		}
 		return make_float2(a * w.x, b * w.y);
 	}
@@ -104,11 +104,12 @@ stft_kernel(StftArgs a, const float2 *__restrict__ tw, float half_scale) {
 		ld.n = a.n;
 		ld.stride = a.x_stride;
 		ld.base = t * a.hop - half_n;
+		ld.origin = a.x_origin;
 		ld.win2 = reinterpret_cast<const float2 *>(a.window);
 		ld.half_n = half_n;
 		ld.valid = valid;
 		ld.fast = a.x_stride == 1 && ld.base >= 0 && ld.base + a.n_fft <= a.n &&
-		          ((reinterpret_cast<uintptr_t>(ld.x + ld.base) & 7) == 0);
+		          ((reinterpret_cast<uintptr_t>(ld.x + (ld.base - ld.origin)) & 7) == 0);
 
 		if (C::INPLACE)
 			stockham_pass_inplace<LOG2M, 0, false>(tid, ld, buf0, tw);
@@ -242,7 +243,7 @@ stft_tma_kernel(StftArgs a, const float2 *__restrict__ tw, float half_scale) {
 		const int64_t t = a.frame0 + (f - ch * a.n_frames);
 		const int64_t base = t * a.hop - half_n;
 		if (base < 0 || base + a.n_fft > a.n) return false;
-		*src = a.x + ch * a.x_ch_stride + base;
+		*src = a.x + ch * a.x_ch_stride + (base - a.x_origin);
 		return true;
 	};
 	auto issue = [&](int64_t f) {        // the slot's thread 0: prefetch the raw samples of frame f
@@ -281,6 +282,7 @@ stft_tma_kernel(StftArgs a, const float2 *__restrict__ tw, float half_scale) {
 			ld.n = a.n;
 			ld.stride = a.x_stride;
 			ld.base = t * a.hop - half_n;
+			ld.origin = a.x_origin;
 			ld.win2 = reinterpret_cast<const float2 *>(a.window);
 			ld.half_n = half_n;
 			ld.valid = true;
@@ -348,6 +350,7 @@ static int launch_tma(const StftArgs &a, int device, cudaStream_t st) {
 
 static bool tma_eligible(const StftArgs &a) {
 	return a.x_stride == 1 && (a.hop & 3) == 0 && ((a.n_fft >> 1) & 3) == 0 && (a.x_ch_stride & 3) == 0 &&
+	       (a.x_origin & 3) == 0 &&
 	       (reinterpret_cast<uintptr_t>(a.x) & 15) == 0;
 }
 

@@ -496,3 +496,61 @@ def test_host_pipeline_chunking_is_invisible(fourier, resampling, monkeypatch):
     monkeypatch.delenv("PAR_B200_CHUNK_BYTES")
     pos = oracle.speed_to_pos_c(curve[:, 0] * sr, curve[:, 1], len(sig))
     _check_sinc(np.ascontiguousarray(ref_v[:, 1]), pos, np.ascontiguousarray(sig[:, 1]), 50)
+
+
+# ----------------------------------------------------------------------------------------- time shards
+@pytest.mark.parametrize("world", [1, 3])
+def test_time_shards_reassemble_to_the_single_gpu_result(par, fourier, resampling, world):
+    """every rank transforms / resamples its chunk + halo through the range entry
+    points; concatenating the ranks' results equals the unsharded call bit for bit."""
+    import torch
+    from pyaudiorestoration_b200 import _lib, dist as pdist
+    dev = torch.device("cuda", _lib.device())
+    sr, n_fft, hop, nt = 96000, 1024, 256, 50
+    n = sr * 2 + 123
+    xs = np.stack([synth(n, 71), synth(n, 72)])                       # (channels, n) planar
+    win = onp.get_window_f32("blackmanharris", n_fft)
+    curve = wow_curve(n / sr, sr, hop, depth=0.03, freq=1.7)
+    pos_np = resampling.speed_to_pos(curve[:, 0] * sr, curve[:, 1], n)
+    pos = torch.from_numpy(np.ascontiguousarray(pos_np)).to(dev)
+    full_S = fourier.stft_multi(xs.T, n_fft, hop)                     # (C, F, T)
+    full_y = resampling.resample_channels(xs.T, pos_np, [0, 1], "Sinc", nt)
+    full_l = resampling.resample_channels(xs.T, pos_np, [0, 1], "Linear")
+    S_parts, y_parts, l_parts, o_prev = [], [], [], 0
+    for rank in range(world):
+        sh = pdist.TimeShard(n, n_fft, hop, nt, rank, world)
+        buf = sh.local_buffer(2, dev)
+        buf.copy_(torch.from_numpy(xs[:, sh.origin:sh.origin + sh.local_len]))   # chunk + halos as exchange_halos leaves them
+        S_parts.append(sh.stft(buf, win).cpu().numpy())
+        o0, o1 = sh.output_range(pos)
+        assert o0 == o_prev
+        o_prev = o1
+        # positions: the rank's own slice (par_speed_to_pos_range_f64) equals the same slice of the full array
+        ps, p0, m_glob = sh.positions(curve[:, 0] * sr, curve[:, 1], dev)
+        assert m_glob == len(pos_np) and p0 <= o0 and p0 + len(ps) >= min(o1 + 1, m_glob)
+        assert np.array_equal(ps.cpu().numpy(), pos_np[p0:p0 + len(ps)])
+        assert sh.output_range(ps, p0, m_glob) == (o0, o1)
+        y_parts.append(sh.resample(buf, ps, "Sinc", pos_origin=p0, m=m_glob).cpu().numpy())
+        l_parts.append(sh.resample(buf, pos, "Linear", (o0, o1)).cpu().numpy())
+    assert o_prev == len(pos_np)
+    S = np.concatenate(S_parts, axis=1).transpose(0, 2, 1)
+    assert np.array_equal(S, full_S)
+    assert np.array_equal(np.concatenate(y_parts, axis=1).T, full_y)
+    assert np.array_equal(np.concatenate(l_parts, axis=1).T, full_l)
+
+
+def test_range_entry_points_reject_uncovered_slices(par):
+    import torch
+    from pyaudiorestoration_b200 import _lib
+    L = _lib.lib()
+    dev = torch.device("cuda", _lib.device())
+    x = torch.zeros(10000, device=dev)
+    out = torch.zeros((100, 513), dtype=torch.complex64, device=dev)
+    win = onp.get_window_f32("hann", 1024)
+    # frames 10..19 need samples from 10*256-512; a slice starting at 4096 does not cover them
+    rc = L.par_stft_range_f32(x.data_ptr(), 10000, 4096, 100000, 1, 10000, 1024, 256, 1, win.ctypes.data, 10, 10,
+                              out.data_ptr(), 513, 0, _lib.PAR_DEVICE_PTRS, dev.index, None)
+    assert rc == -1 and b"cover" in L.par_last_error()
+    rc = L.par_stft_range_f32(x.data_ptr(), 10000, 4096, 100000, 1, 10000, 1024, 256, 1, win.ctypes.data, 10, 10,
+                              out.data_ptr(), 513, 0, 0, dev.index, None)
+    assert rc == -3          # host pointers are not supported by the range entries
