@@ -82,7 +82,8 @@ PAR_API int64_t par_stft_num_frames(int64_t n, int n_fft, int hop);
 /* Fused reflect-pad + frame gather + window + real FFT of length n_fft*zeropad (frame
  * left-aligned, zeros appended) + 1/sqrt(n_fft) scaling, for n_ch channels in one launch.
  * window: HOST float32[n_fft].  out: complex64 (or float32 with PAR_OUT_MAGNITUDE).
- * n_fft*zeropad must be a power of two in [32, 32768]; n >= 1. */
+ * n_fft*zeropad must be a power of two in [32, 1048576] (above 32768: four-step path through an
+ * L2-resident scratch, unit-stride channels only); n >= 1. */
 PAR_API int par_stft_f32(const float *x, int64_t n, int64_t x_stride, int n_ch, int64_t x_ch_stride,
                  int n_fft, int hop, int zeropad, const float *window,
                  void *out, int64_t out_pitch, int64_t out_ch_stride,

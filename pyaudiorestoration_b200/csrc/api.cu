@@ -109,6 +109,31 @@ const float2 *fft_twiddles(int device, int log2m, cudaStream_t st) {
 	return (const float2 *)upload_table(key, tw.data(), tw.size() * sizeof(float2), st);
 }
 
+const float2 *large_fft_tables(int device, int log2m, cudaStream_t st) {
+	std::lock_guard<std::mutex> lk(g_mu);
+	TableKey key{device, 4, log2m, 0};
+	auto it = g_tables.find(key);
+	if (it != g_tables.end()) return (const float2 *)it->second;
+	const int64_t M = (int64_t)1 << log2m;
+	const int64_t n_hi = M >> 10, n_shi = (M >> 10) + 1;     // the split twiddle is used for every k < M
+	std::vector<float2> tab(1024 + n_hi + 1024 + n_shi);
+	for (int64_t p = 0; p < 1024; p++) {
+		const double ang = -2.0 * M_PI * (double)p / (double)M;
+		tab[p] = make_float2((float)cos(ang), (float)sin(ang));
+		const double ang2 = -M_PI * (double)p / (double)M;
+		tab[1024 + n_hi + p] = make_float2((float)cos(ang2), (float)sin(ang2));
+	}
+	for (int64_t q = 0; q < n_hi; q++) {
+		const double ang = -2.0 * M_PI * (double)(q << 10) / (double)M;
+		tab[1024 + q] = make_float2((float)cos(ang), (float)sin(ang));
+	}
+	for (int64_t q = 0; q < n_shi; q++) {
+		const double ang = -M_PI * (double)(q << 10) / (double)M;
+		tab[2048 + n_hi + q] = make_float2((float)cos(ang), (float)sin(ang));
+	}
+	return (const float2 *)upload_table(key, tab.data(), tab.size() * sizeof(float2), st);
+}
+
 static uint64_t fnv1a(const void *p, size_t n) {
 	const unsigned char *b = (const unsigned char *)p;
 	uint64_t h = 1469598103934665603ull;

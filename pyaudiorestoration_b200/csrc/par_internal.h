@@ -20,6 +20,9 @@ int sm_count(int device);
 
 // Device-resident constant tables, cached per (device, key); built on the host in float64.
 const float2 *fft_twiddles(int device, int log2m, cudaStream_t st);          // FftSched<log2m> layout
+// two-level tables of the large (four-step) transform of 2^log2m complex points:
+// [W_M^p, p<1024 | W_M^(1024 q), q<M/1024 | W_2M^k, k<1024 | W_2M^(1024 q), q<=M/1024]
+const float2 *large_fft_tables(int device, int log2m, cudaStream_t st);
 const float *device_window(int device, const float *host_window, int n, cudaStream_t st);
 // sinc tap coefficients: c[k] = (-1)^(k-nt+1) * hanning(2nt+1)[k] / pi  and  hp[k] = hanning[k] / pi,
 // k = 0 .. 2nt-1, each padded with zeros to a multiple of 16 (+16)
@@ -44,6 +47,7 @@ struct StftArgs {
 	int magnitude;
 };
 int launch_stft(const StftArgs &a, int device, cudaStream_t st);
+int launch_stft_large(const StftArgs &a, int log2m, int device, cudaStream_t st);   // 15 <= log2m <= 19
 
 struct IstftArgs {
 	const float2 *S;

@@ -400,11 +400,18 @@ static int dispatch(const StftArgs &a, int log2m, int device, cudaStream_t st) {
 int launch_stft(const StftArgs &a, int device, cudaStream_t st) {
 	const int64_t nz = (int64_t)a.n_fft * a.zeropad;
 	int log2m = -1;
-	for (int b = 4; b <= 14; b++)
+	for (int b = 4; b <= 19; b++)
 		if (nz == (int64_t)2 << b) log2m = b;
 	if (log2m < 0 || (a.n_fft & 1)) {
-		set_error("stft: n_fft*zeropad must be a power of two in [32, 32768] (n_fft even)");
+		set_error("stft: n_fft*zeropad must be a power of two in [32, 1048576] (n_fft even)");
 		return PAR_EUNSUPPORTED;
+	}
+	if (log2m >= 15) {
+		if (a.x_stride != 1) {
+			set_error("stft: transforms above 32768 points need unit-stride channels");
+			return PAR_EUNSUPPORTED;
+		}
+		return launch_stft_large(a, log2m, device, st);
 	}
 	return a.magnitude ? dispatch<true>(a, log2m, device, st) : dispatch<false>(a, log2m, device, st);
 }

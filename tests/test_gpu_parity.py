@@ -116,6 +116,27 @@ def test_stft_sizes(fourier, n_fft, hop):
     _check_stft(s, x, n_fft, hop, "blackmanharris", 1)
 
 
+@pytest.mark.parametrize("n_fft,hop", [(65536, 16384), (131072, 32768), (262144, 131072), (524288, 1048576),
+                                       (1048576, 262144)])
+def test_stft_large_sizes(fourier, n_fft, hop):
+    """Four-step path (N*Z > 32768): the GUIs go up to 1048576 (util/widgets.py:333-335)."""
+    x = synth(3 * n_fft + 4567, n_fft % 1000 + 1)
+    s = fourier.stft(x, n_fft, hop)
+    _check_stft(s, x, n_fft, hop, "blackmanharris", 1)
+    mag = fourier.get_mag(x, n_fft, hop, "hann")
+    truth = np.abs(onp.stft_f64(x, n_fft, hop, "hann").T) + 1e-7
+    assert rel_max(mag, truth) <= TOL
+
+
+def test_stft_large_zeropad_and_multichannel(fourier):
+    sig = np.stack([synth(200000, 81), synth(200000, 82)], axis=1)
+    multi = fourier.stft_multi(sig, 16384, 4096, zeropad=4)              # 65536-point transform
+    for c in range(2):
+        _check_stft(multi[c], np.ascontiguousarray(sig[:, c]), 16384, 4096, "blackmanharris", 4)
+    short = synth(40000, 83)                                             # shorter than the window: both edges reflect
+    _check_stft(fourier.stft(short, 65536, 16384), short, 65536, 16384, "blackmanharris", 1)
+
+
 @pytest.mark.parametrize("n_fft,hop,zp", [(256, 64, 4), (1024, 256, 2), (2048, 512, 16), (64, 16, 8)])
 def test_stft_zeropad(fourier, n_fft, hop, zp):
     x = synth(9000, 31 + zp)
