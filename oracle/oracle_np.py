@@ -276,3 +276,94 @@ def linear_resample(sample_at, signal):
     """The "Linear" mode of run -- util/resampling.py:228-229."""
     return np.interp(sample_at, np.arange(len(signal)), signal, left=0.0, right=0.0).astype(
         np.float32)
+
+
+# --------------------------------------------------------------------------- dropout tools (config 4)
+
+def time_2_frame(t, sr, hop):
+    """dropout_healer_gui.py:99-101."""
+    return int(t * sr / hop)
+
+
+def freq_2_bin(f, fft_size, sr):
+    """dropout_healer_gui.py:107-109."""
+    return max(1, min(fft_size // 2, int(round(f * fft_size / sr))))
+
+
+def heal_regions(markers, sr, fft_size, hop):
+    """Integer regions dropout_healer_gui.py:136-141 derives from markers given as rows
+    ``(t, width, f, height, surrounding)``: ``(frame_b, frame_a, frame_surrounding, bin_l, bin_u)``."""
+    out = []
+    for t, width, f, height, surrounding in np.asarray(markers, dtype=np.float64).tolist():
+        out.append((time_2_frame(t - (width / 2), sr, hop), time_2_frame(t + (width / 2), sr, hop),
+                    max(1, time_2_frame(width * surrounding, sr, hop)),
+                    freq_2_bin(f - (height / 2), fft_size, sr), freq_2_bin(f + (height / 2), fft_size, sr)))
+    return np.array(out, dtype=np.int64).reshape(-1, 5)
+
+
+def heal_ref(x, sr, markers, fft_size, hop):
+    """One channel of dropout_healer_gui.py:124-164 on the CPU: fix_length :129, stft (numpy back-end)
+    :132, dB :133, per-marker means :144-145, bilinear target :148-154, clipped gain :156-160,
+    ``S *= 10**(gain/20)`` :162, istft :164.  Pinned by tests/golden/dropouts.npz, which holds the
+    output of the unmodified reference method."""
+    from scipy.interpolate import RegularGridInterpolator
+    x = np.asarray(x, dtype=np.float32)
+    n = len(x)
+    y_pad = fix_length(x, n + fft_size // 2)
+    spec = np.array(stft_ref(y_pad, fft_size, hop))
+    spec_db = 20 * np.log10(to_mag(spec))
+    gain = np.zeros(spec.shape, dtype=float)
+    for frame_b, frame_a, around, bin_l, bin_u in heal_regions(markers, sr, fft_size, hop).tolist():
+        mag_before = np.mean(spec_db[bin_l:bin_u, frame_b - around:frame_b], axis=1)
+        mag_after = np.mean(spec_db[bin_l:bin_u, frame_a:frame_a + around], axis=1)
+        fp_frames = np.linspace(frame_b, frame_a, num=frame_a - frame_b)
+        fp_bins = np.linspace(bin_l, bin_u, num=bin_u - bin_l)
+        interp = RegularGridInterpolator(((frame_b, frame_a), fp_bins), (mag_before, mag_after))
+        mp_bins, mp_frames = np.meshgrid(fp_bins, fp_frames)
+        fp_db = np.swapaxes(interp((mp_frames, mp_bins)), 0, 1)
+        g = fp_db - spec_db[bin_l:bin_u, frame_b:frame_a]
+        np.clip(g, gain[bin_l:bin_u, frame_b:frame_a], 255, out=g)
+        gain[bin_l:bin_u, frame_b:frame_a] = g
+    spec = spec * np.power(10, gain / 20)
+    return istft_ref(spec, hop_length=hop, length=n).astype(np.float32)
+
+
+def locate_peaks_ref(magnitude, sr, fft_size, hop, t_0, t_1, f_lower, f_upper, sensitivity):
+    """Integer frame indices of dropout_healer_gui.py:188-204: dB, band/time window, mean over the
+    band, ``find_peaks(-vol, prominence=10-sensitivity)``."""
+    import scipy.signal
+    imdata = 20 * np.log10(np.array(magnitude))
+    frame_b, frame_a = time_2_frame(t_0, sr, hop), time_2_frame(t_1, sr, hop)
+    bin_l, bin_u = freq_2_bin(f_lower, fft_size, sr), freq_2_bin(f_upper, fft_size, sr)
+    vol = np.mean(imdata[bin_l:bin_u, frame_b:frame_a], axis=0)
+    peaks, _ = scipy.signal.find_peaks(-vol, height=None, threshold=None, distance=None,
+                                       prominence=10.0 - sensitivity, wlen=None, rel_height=0.5, plateau_size=None)
+    return peaks
+
+
+def max_mono_ref(signal, fft_size, hop):
+    """dropouts_gui.py:137-163 on the CPU: ``{"max": y, "min": y}``."""
+    n = len(signal)
+    y_pad = fix_length(np.asarray(signal), n + fft_size // 2, axis=0)
+    d_l = np.array(stft_ref(y_pad[:, 0], fft_size, hop))
+    d_r = np.array(stft_ref(y_pad[:, 1], fft_size, hop))
+    out = {}
+    for name, mask in (("max", np.abs(d_l) > np.abs(d_r)), ("min", np.abs(d_l) < np.abs(d_r))):
+        out[name] = istft_ref(np.where(mask, d_l, d_r), hop_length=hop, length=n)
+    return out
+
+
+def heuristic_peaks_ref(magnitude, sr, fft_size, f_lower, f_upper, num_bands):
+    """Per-band integer peak lists of dropouts_gui.py:251, :264-288, top band first."""
+    import scipy.signal
+    imdata = 20 * np.log10(np.array(magnitude))
+    bands = np.logspace(np.log2(f_lower), np.log2(f_upper), num=num_bands, endpoint=True, base=2, dtype=np.uint16)
+    pairs = list(zip(bands[:-1], bands[1:]))
+    out = []
+    for f_lower_band, f_upper_band in reversed(pairs):
+        bin_lower = int(f_lower_band * fft_size / sr)
+        bin_upper = int(f_upper_band * fft_size / sr)
+        vol = np.mean(imdata[bin_lower:bin_upper], axis=0)
+        peaks, _ = scipy.signal.find_peaks(-vol, prominence=5, rel_height=0.5)
+        out.append(peaks)
+    return out

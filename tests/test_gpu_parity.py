@@ -575,3 +575,60 @@ def test_range_entry_points_reject_uncovered_slices(par):
     rc = L.par_stft_range_f32(x.data_ptr(), 10000, 4096, 100000, 1, 10000, 1024, 256, 1, win.ctypes.data, 10, 10,
                               out.data_ptr(), 513, 0, 0, dev.index, None)
     assert rc == -3          # host pointers are not supported by the range entries
+
+
+# ----------------------------------------------------------------------------------------- BASELINE configs 1 and 4
+def test_cfg1_flutter_stft_matches_reference(golden_dir, fourier):
+    """samples/flutter.flac, n_fft 4096 / hop 1024: against frames of the reference's own output."""
+    z = _load(golden_dir, "flutter")
+    x = (z["pcm"].astype(np.float64) / 32768.0).astype(np.float32)
+    s = fourier.stft(x, 4096, 1024)
+    assert s.shape == tuple(z["shape"])
+    _check_stft(s, x, 4096, 1024, "blackmanharris", 1)
+    assert rel_l2(s[:, z["frames"]], z["S"]) <= TOL
+    energy = np.sum(np.abs(s.astype(np.complex128)) ** 2, axis=0)
+    assert np.max(np.abs(energy - z["frame_energy"]) / z["frame_energy"]) <= 2 * TOL
+
+
+def test_cfg4_dropout_heal_and_locate(golden_dir, fourier):
+    """dropouts_sample excerpt: heal against the unmodified reference's output; locator peaks
+    (integer frame indices) bit-exact against the CPU oracle."""
+    from pyaudiorestoration_b200 import dropouts
+    z = _load(golden_dir, "dropouts")
+    x = (z["pcm"].astype(np.float64) / 32768.0).astype(np.float32)
+    sr, fft_size, hop = int(z["sr"]), int(z["fft_size"]), int(z["hop"])
+    drops = [dropouts.Dropout(*m) for m in z["markers"].tolist()]
+    y = dropouts.heal(x[:, None], sr, drops, fft_size, hop, channels=[0])[:, 0]
+    ref = z["healed"]
+    assert y.dtype == np.float32 and y.shape == ref.shape
+    assert rel_max(y, ref) <= TOL and rel_l2(y.astype(np.float64), ref.astype(np.float64)) <= TOL
+    # locator: magnitudes from the GPU, peaks must equal the ones found on the CPU magnitudes
+    mag = fourier.get_mag(x, fft_size, hop, "blackmanharris", 1)
+    cpu_mag = onp.to_mag(onp.stft_ref(x, fft_size, hop))
+    dur = len(x) / sr
+    for sens in (2.0, 4.0, 6.0):
+        peaks, found = dropouts.locate(mag, sr, fft_size, hop, 0.1, dur - 0.1, 768.0, 13723.0, sensitivity=sens)
+        want = onp.locate_peaks_ref(cpu_mag, sr, fft_size, hop, 0.1, dur - 0.1, 768.0, 13723.0, sens)
+        assert peaks.dtype.kind == "i" and np.array_equal(peaks, want)
+        assert len(found) == len(peaks)
+    assert len(want) >= 10                                       # the excerpt really has dropouts to find
+    # batch tool: band-wise valleys on the Hann spectrogram (dropouts_gui.py:264-288)
+    mag_h = fourier.get_mag(x, fft_size, hop, "hann")
+    cpu_h = onp.to_mag(onp.stft_ref(x, fft_size, hop, "hann"))
+    got = dropouts.heuristic_band_peaks(dropouts.to_dB(np.array(mag_h)), sr, fft_size, 100, 15000, 5)
+    want_h = onp.heuristic_peaks_ref(cpu_h, sr, fft_size, 100, 15000, 5)
+    assert len(got) == len(want_h) == 4
+    for g, w in zip(got, want_h):
+        assert np.array_equal(g[4], w)
+    out = dropouts.heuristic(x[:40000, None], sr, fft_size, hop)
+    assert out.shape == (40000, 1) and np.isfinite(out).all()
+
+
+def test_cfg4_max_mono(fourier):
+    from pyaudiorestoration_b200 import dropouts
+    sig = np.stack([synth(30000, 91, 44100.0), synth(30000, 92, 44100.0)], axis=1)
+    got = dropouts.max_mono(sig, 512, 32)
+    want = onp.max_mono_ref(sig, 512, 32)
+    for k in ("max", "min"):
+        # a cell flips channel only if |L| and |R| agree to float32 rounding; allow a handful of such cells
+        assert rel_l2(got[k].astype(np.float64), want[k].astype(np.float64)) <= 5e-6

@@ -1,0 +1,75 @@
+"""CPU tests around the hot path's data formats and the dropout tools' oracle (no GPU):
+FLAC decode (MD5-checked on the reference's samples when they are present, and on synthetic
+streams anywhere), and the oracle restatements pinned by the golden output of the UNMODIFIED
+reference (tests/golden/dropouts.npz, flutter.npz <- tests/golden/make_golden_dropouts.py)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle_np as onp
+from pyaudiorestoration_b200.util import flac, io_ops
+
+from flac_writer import write_flac
+
+REF_SAMPLES = "/root/reference/samples"
+
+
+@pytest.mark.parametrize("bps,channels,mid_side", [(16, 1, False), (16, 2, False), (16, 2, True), (24, 2, True), (8, 3, False)])
+def test_flac_decoder_on_synthetic_streams(tmp_path, bps, channels, mid_side):
+    rng = np.random.default_rng(bps + channels)
+    lim = 1 << (bps - 2)
+    pcm = [rng.integers(-lim, lim, 2500).tolist() for _ in range(channels)]
+    pcm[0][1000:2000] = [pcm[0][1000]] * 1000                    # a CONSTANT subframe
+    data = write_flac(pcm, 48000, bps=bps, blocksize=1000, mid_side=mid_side)
+    got, sr, b = flac.decode_flac(data, verify_md5=True)
+    assert sr == 48000 and b == bps and got.shape == (2500, channels)
+    assert np.array_equal(got.T, np.array(pcm))
+    p = tmp_path / "x.flac"
+    p.write_bytes(data)
+    sig, sr2, ch = io_ops.read_file(str(p))                      # util/io_ops.py:7-16 contract
+    assert sig.dtype == np.float32 and sig.shape == (2500, channels) and ch == channels and sr2 == 48000
+    assert np.array_equal(sig, (np.array(pcm).T / float(1 << (bps - 1))).astype(np.float32))
+    corrupted = bytearray(data)
+    corrupted[-10] ^= 0x40
+    with pytest.raises(ValueError):
+        flac.decode_flac(bytes(corrupted))
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SAMPLES), reason="reference samples only exist in the authoring container")
+def test_flac_decoder_on_reference_samples():
+    files = sorted(glob.glob(os.path.join(REF_SAMPLES, "*.flac")))
+    assert len(files) >= 3
+    for f in files[:3]:                                          # Rice + fixed/LPC subframes; MD5 pins the decode
+        sig, sr, ch = flac.read_flac(f, verify_md5=True)
+        assert ch == 1 and sr in (44100, 192000) and len(sig) > 100000
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "flutter.npz"))
+    pcm, _, _ = flac.decode_flac(open(os.path.join(REF_SAMPLES, "flutter.flac"), "rb").read())
+    assert np.array_equal(pcm[:, 0], z["pcm"])
+
+
+def test_cfg1_oracle_matches_reference_on_flutter(golden_dir):
+    """BASELINE config 1: util.fourier.stft(n_fft=4096, hop=1024) on samples/flutter.flac."""
+    z = np.load(os.path.join(golden_dir, "flutter.npz"))
+    x = (z["pcm"].astype(np.float64) / 32768.0).astype(np.float32)
+    s = onp.stft_ref(x, 4096, 1024)
+    assert tuple(z["shape"]) == s.shape == (2049, len(x) // 1024 + 1)
+    assert np.array_equal(s[:, z["frames"]].astype(np.complex64), z["S"])
+    assert np.allclose(np.sum(np.abs(s) ** 2, axis=0), z["frame_energy"], rtol=1e-12)
+
+
+def test_cfg4_oracle_heal_matches_reference_bitwise(golden_dir):
+    """BASELINE config 4: the oracle's heal reproduces the unmodified dropout_healer_gui body."""
+    z = np.load(os.path.join(golden_dir, "dropouts.npz"))
+    x = (z["pcm"].astype(np.float64) / 32768.0).astype(np.float32)
+    sr, fft_size, hop = int(z["sr"]), int(z["fft_size"]), int(z["hop"])
+    assert np.array_equal(onp.heal_regions(z["markers"], sr, fft_size, hop), z["regions"])
+    assert z["regions"].shape == (25, 5)
+    y = onp.heal_ref(x, sr, z["markers"], fft_size, hop)
+    assert y.dtype == np.float32 and np.array_equal(y, z["healed"])
+    assert np.max(np.abs(y - x)) > 0.01                           # the markers did change the audio
+    # product-side integer rules agree with the reference's (no GPU needed for these)
+    from pyaudiorestoration_b200 import dropouts
+    regs = [dropouts.marker_region(dropouts.Dropout(*m), sr, fft_size, hop) for m in z["markers"].tolist()]
+    assert np.array_equal(np.array(regs), z["regions"])
