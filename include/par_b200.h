@@ -69,6 +69,11 @@ PAR_API int64_t par_kernel_launch_count(void);
  * calling thread (0 if none); informational. */
 PAR_API double par_last_kernel_ms(void);
 
+/* Device self-test of the positions kernels' exact quotient j/(n-1) (three FMAs instead of a
+ * division, csrc/resample.cu SegDiv): compares it with the IEEE division for every j < n,
+ * n = 2 .. max_n.  Returns the number of mismatches (0 expected), -1 on error. */
+PAR_API int64_t par_selftest_positions_quotient(int64_t max_n, int device);
+
 /* Pinned host allocations (the Python layer returns ndarrays backed by these so that the
  * device->host copy of a result runs at full PCIe rate). */
 PAR_API void *par_host_alloc(int64_t bytes);

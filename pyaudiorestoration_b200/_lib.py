@@ -22,7 +22,7 @@ PAR_MODE_SINC = 1
 
 EXPORTS = (
     "par_last_error", "par_version", "par_device_count", "par_kernel_launch_count",
-    "par_last_kernel_ms", "par_host_alloc", "par_host_free", "par_stft_num_frames", "par_stft_f32",
+    "par_last_kernel_ms", "par_selftest_positions_quotient", "par_host_alloc", "par_host_free", "par_stft_num_frames", "par_stft_f32",
     "par_istft_f32", "par_speed_segments", "par_speed_to_pos_f64", "par_sinc_resample_f32",
     "par_linear_resample_f32", "par_varispeed_f32", "par_stft_range_f32", "par_resample_range_f32", "par_speed_to_pos_range_f64",
 )
@@ -47,6 +47,8 @@ def _declare(L):
     L.par_device_count.restype = i32
     L.par_kernel_launch_count.restype = i64
     L.par_last_kernel_ms.restype = dbl
+    L.par_selftest_positions_quotient.restype = i64
+    L.par_selftest_positions_quotient.argtypes = [i64, i32]
     L.par_host_alloc.restype = vp
     L.par_host_alloc.argtypes = [i64]
     L.par_host_free.restype = None

@@ -410,6 +410,20 @@ PAR_API int par_device_count(void) {
 PAR_API int64_t par_kernel_launch_count(void) { return g_launches.load(); }
 PAR_API double par_last_kernel_ms(void) { return g_last_ms; }
 
+PAR_API int64_t par_selftest_positions_quotient(int64_t max_n, int device) {
+	if (use_device(device) != PAR_OK) return -1;
+	unsigned long long *d = nullptr, h = 0;
+	if (cudaMalloc(&d, sizeof(h)) != cudaSuccess) { cuda_fail(cudaGetLastError(), "cudaMalloc"); return -1; }
+	cudaMemset(d, 0, sizeof(h));
+	int rc = launch_quotient_selftest(max_n, d, nullptr);
+	if (rc == PAR_OK && cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) {
+		cuda_fail(cudaGetLastError(), "selftest");
+		rc = PAR_ECUDA;
+	}
+	cudaFree(d);
+	return rc == PAR_OK ? (int64_t)h : -1;
+}
+
 PAR_API void *par_host_alloc(int64_t bytes) {
 	void *p = nullptr;
 	if (bytes <= 0) bytes = 16;
@@ -609,8 +623,16 @@ static int positions_device(const double *sampletimes, const double *speeds, int
 	PAR_CUDA(cudaMemcpyAsync(d_sp.p, speeds, k * sizeof(double), cudaMemcpyHostToDevice, st));
 	PAR_CUDA(cudaMemcpyAsync(d_n.p, seg_n.data(), n_seg * sizeof(int64_t), cudaMemcpyHostToDevice, st));
 	PAR_CUDA(cudaMemcpyAsync(d_start.p, seg_start.data(), n_seg * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-	if ((rc = launch_segment_sums(d_sp.as<double>(), d_n.as<int64_t>(), n_seg, d_sum.as<double>(), st)) != PAR_OK)
-		return rc;
+	// whole-curve call: ONE pass writes every segment's bare cumsum into pos (capacity permitting) and
+	// its total; after the host chain a streaming pass adds the offsets.  Windowed call (shards):
+	// totals only, then expand just the window's segments.
+	const bool one_pass = !window && cap >= total;
+	if (one_pass)
+		rc = launch_expand_positions(d_sp.as<double>(), d_n.as<int64_t>(), d_start.as<int64_t>(), nullptr, n_seg, pos,
+		                             total, st, d_sum.as<double>());
+	else
+		rc = launch_segment_sums(d_sp.as<double>(), d_n.as<int64_t>(), n_seg, d_sum.as<double>(), st);
+	if (rc != PAR_OK) return rc;
 	std::vector<double> sums(n_seg), off(n_seg);
 	PAR_CUDA(cudaMemcpyAsync(sums.data(), d_sum.p, n_seg * sizeof(double), cudaMemcpyDeviceToHost, st));
 	PAR_CUDA(cudaStreamSynchronize(st));
@@ -673,8 +695,11 @@ static int positions_device(const double *sampletimes, const double *speeds, int
 	if (m == 0) return PAR_OK;
 	if (chain) { chain->start = seg_start; chain->off = off; }
 	PAR_CUDA(cudaMemcpyAsync(d_off.p, off.data(), n_seg * sizeof(double), cudaMemcpyHostToDevice, st));
-	rc = launch_expand_positions(d_sp.as<double>() + seg_a, d_n.as<int64_t>() + seg_a, d_start.as<int64_t>() + seg_a,
-	                             d_off.as<double>() + seg_a, seg_b - seg_a, pos, m, st);
+	if (one_pass)
+		rc = launch_add_offsets(d_n.as<int64_t>(), d_start.as<int64_t>(), d_off.as<double>(), n_seg, pos, m, st);
+	else
+		rc = launch_expand_positions(d_sp.as<double>() + seg_a, d_n.as<int64_t>() + seg_a, d_start.as<int64_t>() + seg_a,
+		                             d_off.as<double>() + seg_a, seg_b - seg_a, pos, m, st);
 	if (rc != PAR_OK) return rc;
 	// `off` (pageable) must outlive its async copy
 	PAR_CUDA(cudaStreamSynchronize(st));

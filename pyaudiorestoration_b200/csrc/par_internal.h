@@ -62,11 +62,15 @@ struct IstftArgs {
 };
 int launch_istft(const IstftArgs &a, int device, cudaStream_t st);
 
+int launch_quotient_selftest(int64_t max_n, unsigned long long *mismatches_dev, cudaStream_t st);
 int launch_segment_sums(const double *speeds_dev, const int64_t *seg_n_dev, int64_t n_seg,
                         double *sums_dev, cudaStream_t st);
 int launch_expand_positions(const double *speeds_dev, const int64_t *seg_n_dev,
                             const int64_t *seg_start_dev, const double *seg_offset_dev,
-                            int64_t n_seg, double *pos_dev, int64_t m, cudaStream_t st);
+                            int64_t n_seg, double *pos_dev, int64_t m, cudaStream_t st,
+                            double *sums_out_dev = nullptr);
+int launch_add_offsets(const int64_t *seg_n_dev, const int64_t *seg_start_dev, const double *seg_offset_dev,
+                       int64_t n_seg, double *pos_dev, int64_t m, cudaStream_t st);
 
 struct SincArgs {
 	const double *pos;

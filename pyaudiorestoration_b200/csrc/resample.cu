@@ -27,8 +27,28 @@ namespace par {
 
 // v_j and the running sum exactly as np.arange(n)/(n-1)*(s1-s0)+s0 and np.cumsum(1/v) evaluate
 // them (util/resampling.py:120,125): IEEE double ops, no FMA contraction.
-__device__ __forceinline__ double seg_speed(int64_t j, double nm1, double ds, double s0) {
-	return __dadd_rn(__dmul_rn(__ddiv_rn((double)j, nm1), ds), s0);
+// The quotient j/(n-1) is needed for every element but its divisor is fixed per segment: with
+// rcp = RN(1/(n-1)), q0 = RN(j*rcp), the exact remainder r = j - q0*(n-1) (one FMA) and
+// q = RN(q0 + r*rcp) give the correctly rounded quotient (Markstein's final-correction step, the
+// same one the hardware division sequence ends with) at the cost of three FMA-class operations.
+struct SegDiv {
+	double nm1, rcp;
+	bool exact;       // n - 1 >= 1: the correction step applies; otherwise fall back to a true division
+	__device__ __forceinline__ explicit SegDiv(int64_t n) {
+		nm1 = (double)(n - 1);
+		exact = n >= 2;
+		rcp = exact ? __ddiv_rn(1.0, nm1) : 0.0;
+	}
+	__device__ __forceinline__ double quot(double j) const {
+		if (!exact) return __ddiv_rn(j, nm1);
+		const double q0 = __dmul_rn(j, rcp);
+		const double r = __fma_rn(-q0, nm1, j);
+		return __fma_rn(r, rcp, q0);
+	}
+};
+
+__device__ __forceinline__ double seg_speed(int64_t j, const SegDiv &sd, double ds, double s0) {
+	return __dadd_rn(__dmul_rn(sd.quot((double)j), ds), s0);
 }
 
 __global__ void __launch_bounds__(128)
@@ -39,7 +59,7 @@ segment_sums_kernel(const double *__restrict__ speeds, const int64_t *__restrict
 	const int64_t n = seg_n[i];
 	const double s0 = speeds[i];
 	const double ds = __dsub_rn(speeds[i + 1], s0);
-	const double nm1 = (double)(n - 1);
+	const SegDiv nm1(n);
 	double acc = 0.0;
 	int64_t j = 0;
 	for (; j + 8 <= n; j += 8) {      // the divisions are independent: let them pipeline
@@ -60,12 +80,15 @@ constexpr int EXP_WARPS = 4;
 __global__ void __launch_bounds__(32 * EXP_WARPS)
 expand_positions_kernel(const double *__restrict__ speeds, const int64_t *__restrict__ seg_n,
                         const int64_t *__restrict__ seg_start, const double *__restrict__ seg_off,
-                        int64_t n_seg, double *__restrict__ pos, int64_t m) {
+                        int64_t n_seg, double *__restrict__ pos, int64_t m, double *__restrict__ sums_out) {
+	// seg_off == nullptr: write the bare per-segment cumsum (offset 0) and its total to sums_out;
+	// add_offsets_kernel finishes the job once the host has chained the offsets
 	__shared__ double tile[EXP_WARPS][32][33];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
 	int64_t start = 0, n = 0;
-	double s0 = 1.0, ds = 0.0, nm1 = 1.0, off = 0.0;
+	double s0 = 1.0, ds = 0.0, off = 0.0;
+	int64_t n_full = 2;
 	if (i < n_seg) {
 		start = seg_start[i];
 		n = seg_n[i];
@@ -73,9 +96,11 @@ expand_positions_kernel(const double *__restrict__ speeds, const int64_t *__rest
 		if (start + n > m) n = m - start;
 		s0 = speeds[i];
 		ds = __dsub_rn(speeds[i + 1], s0);
-		nm1 = (double)(seg_n[i] - 1);
-		off = seg_off[i];
+		n_full = seg_n[i];
+		off = seg_off ? seg_off[i] : 0.0;
+		if (sums_out) n = n_full > 0 ? n_full : 0;      // the total needs the whole segment
 	}
+	const SegDiv nm1(n_full);
 	int64_t nmax = n;
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
@@ -87,25 +112,52 @@ expand_positions_kernel(const double *__restrict__ speeds, const int64_t *__rest
 			for (int jj = 0; jj < 32; jj++) r[jj] = __ddiv_rn(1.0, seg_speed(j0 + jj, nm1, ds, s0));
 #pragma unroll
 			for (int jj = 0; jj < 32; jj++) {
-				acc = __dadd_rn(acc, r[jj]);
-				tile[warp][lane][jj] = __dadd_rn(acc, off);
+				if (j0 + jj < n) acc = __dadd_rn(acc, r[jj]);
+				tile[warp][lane][jj] = seg_off ? __dadd_rn(acc, off) : acc;
 			}
 		}
 		__syncwarp();
 		for (int row = 0; row < 32; row++) {
 			const int64_t rn = __shfl_sync(0xffffffffu, n, row);
 			const int64_t rs = __shfl_sync(0xffffffffu, start, row);
-			if (j0 + lane < rn) pos[rs + j0 + lane] = tile[warp][row][lane];
+			if (j0 + lane < rn && rs + j0 + lane < m) pos[rs + j0 + lane] = tile[warp][row][lane];
 		}
 		__syncwarp();
 	}
+	if (sums_out && i < n_seg) sums_out[i] = acc;
 }
 
-int launch_segment_sums(const double *speeds_dev, const int64_t *seg_n_dev, int64_t n_seg,
-                        double *sums_dev, cudaStream_t st) {
-	if (n_seg <= 0) return PAR_OK;
-	segment_sums_kernel<<<(unsigned)((n_seg + 127) / 128), 128, 0, st>>>(speeds_dev, seg_n_dev, n_seg,
-	                                                                      sums_dev);
+// pos[start_i + j] = cumsum_j + off_i for every segment i (np.cumsum(...) + offset,
+// util/resampling.py:125): one warp per segment, lanes streaming it with independent accesses.
+__global__ void __launch_bounds__(256)
+add_offsets_kernel(const int64_t *__restrict__ seg_n, const int64_t *__restrict__ seg_start,
+                   const double *__restrict__ seg_off, int64_t n_seg, double *__restrict__ pos, int64_t m) {
+	const int lane = threadIdx.x & 31;
+	for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; i < n_seg;
+	     i += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+		const int64_t start = seg_start[i];
+		int64_t n = seg_n[i];
+		if (start + n > m) n = m - start;
+		const double off = seg_off[i];
+		double *p = pos + start;
+		int64_t j = lane;
+		for (; j + 96 < n; j += 128) {
+			const double a = p[j], b = p[j + 32], c = p[j + 64], d = p[j + 96];
+			p[j] = __dadd_rn(a, off);
+			p[j + 32] = __dadd_rn(b, off);
+			p[j + 64] = __dadd_rn(c, off);
+			p[j + 96] = __dadd_rn(d, off);
+		}
+		for (; j < n; j += 32) p[j] = __dadd_rn(p[j], off);
+	}
+}
+
+int launch_add_offsets(const int64_t *seg_n_dev, const int64_t *seg_start_dev, const double *seg_offset_dev,
+                       int64_t n_seg, double *pos_dev, int64_t m, cudaStream_t st) {
+	if (n_seg <= 0 || m <= 0) return PAR_OK;
+	int64_t blocks = (n_seg + 7) / 8;                 // 8 warps per block, one warp per segment
+	if (blocks > 148 * 32) blocks = 148 * 32;
+	add_offsets_kernel<<<(unsigned)blocks, 256, 0, st>>>(seg_n_dev, seg_start_dev, seg_offset_dev, n_seg, pos_dev, m);
 	count_launch();
 	PAR_CUDA(cudaGetLastError());
 	return PAR_OK;
@@ -113,11 +165,11 @@ int launch_segment_sums(const double *speeds_dev, const int64_t *seg_n_dev, int6
 
 int launch_expand_positions(const double *speeds_dev, const int64_t *seg_n_dev,
                             const int64_t *seg_start_dev, const double *seg_offset_dev,
-                            int64_t n_seg, double *pos_dev, int64_t m, cudaStream_t st) {
-	if (n_seg <= 0 || m <= 0) return PAR_OK;
+                            int64_t n_seg, double *pos_dev, int64_t m, cudaStream_t st, double *sums_out_dev) {
+	if (n_seg <= 0 || (m <= 0 && !sums_out_dev)) return PAR_OK;
 	const int tpb = 32 * EXP_WARPS;
 	expand_positions_kernel<<<(unsigned)((n_seg + tpb - 1) / tpb), tpb, 0, st>>>(
-	    speeds_dev, seg_n_dev, seg_start_dev, seg_offset_dev, n_seg, pos_dev, m);
+	    speeds_dev, seg_n_dev, seg_start_dev, seg_offset_dev, n_seg, pos_dev, m, sums_out_dev);
 	count_launch();
 	PAR_CUDA(cudaGetLastError());
 	return PAR_OK;

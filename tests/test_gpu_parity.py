@@ -276,6 +276,23 @@ def test_speed_to_pos_matches_oracle_long(resampling):
     assert np.array_equal(pos, oracle.speed_to_pos_c(np.array([0., 8000.]), np.array([.5, 2.]), 8000))
 
 
+def test_positions_quotient_is_the_ieee_quotient(par):
+    """The positions kernels replace j/(n-1) by q0 = j*rcp, r = fma(-q0, n-1, j), q = fma(r, rcp, q0);
+    exhaustive device check against the IEEE division for every segment length up to 40000."""
+    from pyaudiorestoration_b200 import _lib
+    assert _lib.lib().par_selftest_positions_quotient(40000, _lib.device()) == 0
+
+
+def test_speed_to_pos_many_segment_lengths(resampling):
+    rng = np.random.default_rng(3)
+    lens = np.concatenate([[2, 3, 4, 5, 1023, 1024, 1025, 2047, 2048, 4095, 4096, 8191], rng.integers(2, 6000, 150)])
+    st = np.concatenate([[0.0], np.cumsum(lens.astype(np.float64))])
+    sp = 1 + 0.3 * rng.uniform(-1, 1, len(st))
+    pos = resampling.speed_to_pos(st, sp, 10 ** 9)
+    ref = oracle.speed_to_pos_c(st, sp, 10 ** 9)
+    assert len(pos) == len(ref) and np.array_equal(pos, ref)
+
+
 # ----------------------------------------------------------------------------------------- resampler
 def _check_sinc(y, pos, x, nt):
     truth = oracle.sinc_c(pos, x, nt)       # float64 arithmetic, float32 store
