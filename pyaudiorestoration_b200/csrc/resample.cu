@@ -152,6 +152,34 @@ add_offsets_kernel(const int64_t *__restrict__ seg_n, const int64_t *__restrict_
 	}
 }
 
+// Self-test of SegDiv::quot against the IEEE division for every j < n, n = 2 .. max_n.
+__global__ void quotient_selftest_kernel(int64_t max_n, unsigned long long *mismatches) {
+	unsigned long long bad = 0;
+	for (int64_t n = 2 + blockIdx.x; n <= max_n; n += gridDim.x) {
+		const SegDiv sd(n);
+		for (int64_t j = threadIdx.x; j < n; j += blockDim.x)
+			if (sd.quot((double)j) != __ddiv_rn((double)j, sd.nm1)) bad++;
+	}
+	if (bad) atomicAdd(mismatches, bad);
+}
+
+int launch_quotient_selftest(int64_t max_n, unsigned long long *mismatches_dev, cudaStream_t st) {
+	quotient_selftest_kernel<<<1184, 256, 0, st>>>(max_n, mismatches_dev);
+	count_launch();
+	PAR_CUDA(cudaGetLastError());
+	return PAR_OK;
+}
+
+int launch_segment_sums(const double *speeds_dev, const int64_t *seg_n_dev, int64_t n_seg,
+                        double *sums_dev, cudaStream_t st) {
+	if (n_seg <= 0) return PAR_OK;
+	segment_sums_kernel<<<(unsigned)((n_seg + 127) / 128), 128, 0, st>>>(speeds_dev, seg_n_dev, n_seg,
+	                                                                      sums_dev);
+	count_launch();
+	PAR_CUDA(cudaGetLastError());
+	return PAR_OK;
+}
+
 int launch_add_offsets(const int64_t *seg_n_dev, const int64_t *seg_start_dev, const double *seg_offset_dev,
                        int64_t n_seg, double *pos_dev, int64_t m, cudaStream_t st) {
 	if (n_seg <= 0 || m <= 0) return PAR_OK;
@@ -303,6 +331,19 @@ __device__ __forceinline__ void tap_block(const SampleSetup &su, int b, int nt, 
 		const float4 ta = t4[2 * hh], tb = t4[2 * hh + 1];
 		const float coef[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
 		float w[8];
+		if (!LOWPASS && !near) {
+			// far taps of the fc == 1 path: one reciprocal serves two neighbouring taps,
+			//   1/q = (q+1) * t,  1/(q+1) = q * t,  t = 1/(q (q+1)),
+			// which halves the load on the MUFU pipe (the limiter of this path); |q| >= 15.5 here,
+			// so the extra roundings cost ~2e-7 relative on weights below 0.02
+#pragma unroll
+			for (int u = 0; u < 8; u += 2) {
+				const float q = base + (float)(8 * hh + u);
+				const float t = rcp_approx(fmaf(q, q, q));
+				w[u] = fmaf(coef[u], q, coef[u]) * t;
+				w[u + 1] = (coef[u + 1] * q) * t;
+			}
+		} else
 #pragma unroll
 		for (int u = 0; u < 8; u++) {
 			const int j = 8 * hh + u;
