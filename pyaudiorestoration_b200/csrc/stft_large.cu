@@ -19,6 +19,9 @@
 namespace par {
 
 constexpr int LG_CB = 16;          // adjacent columns (kernel A) / rows (kernel B) per CTA
+// slots are S::BUF + 1 float2 apart: lanes that read the same index of 16 different slots (the
+// coalesced epilogues below) then fall into 16 different bank pairs
+template <int LOG2M> constexpr int slot_stride() { return FftSched<LOG2M>::BUF + 1; }
 
 struct BlockSync {
 	__device__ __forceinline__ void operator()() const { __syncthreads(); }
@@ -73,7 +76,7 @@ stft_large_cols_kernel(StftArgs a, int log2m2, int64_t batch0, const float2 *__r
 	using S = FftSched<LOG2M1>;
 	extern __shared__ __align__(16) float2 smem[];
 	const int slot = threadIdx.x / S::TPF, tid = threadIdx.x % S::TPF;
-	float2 *buf = smem + slot * S::BUF;
+	float2 *buf = smem + slot * slot_stride<LOG2M1>();
 	const int m2 = 1 << log2m2;
 	const int tiles = m2 / LG_CB;
 	const int64_t fb = blockIdx.x / tiles;                 // frame within the batch (all channels)
@@ -96,10 +99,14 @@ stft_large_cols_kernel(StftArgs a, int log2m2, int64_t batch0, const float2 *__r
 	stockham_pass_slot<LOG2M1, 0, false>(tid, ld, buf, tw1, sync);
 	RunPassesSlot<LOG2M1, false, 1, BlockSync>::run(tid, buf, tw1, sync);
 	__syncthreads();
-	float2 *dst = scratch + ((size_t)fb << (LOG2M1 + log2m2)) + n2;
-	for (int k1 = tid; k1 < S::M; k1 += S::TPF) {
-		const float2 w = tw2(lt.t_lo, lt.t_hi, k1 * n2);
-		dst[(size_t)k1 << log2m2] = cmul(buf[pad16(k1)], w);
+	// store with 16 consecutive lanes on 16 adjacent columns: 128-byte runs of scratch[k1][n2..n2+15]
+	const int col = threadIdx.x & (LG_CB - 1);
+	const int n2c = n2 - slot + col;
+	float2 *dst = scratch + ((size_t)fb << (LOG2M1 + log2m2)) + n2c;
+	const float2 *src = smem + col * slot_stride<LOG2M1>();
+	for (int k1 = threadIdx.x / LG_CB; k1 < S::M; k1 += S::TPF) {
+		const float2 w = tw2(lt.t_lo, lt.t_hi, k1 * n2c);
+		dst[(size_t)k1 << log2m2] = cmul(src[pad16(k1)], w);
 	}
 }
 
@@ -115,7 +122,7 @@ stft_large_rows_kernel(StftArgs a, int log2m1, int64_t batch0, const float2 *__r
 	using S = FftSched<LOG2M2>;
 	extern __shared__ __align__(16) float2 smem[];
 	const int slot = threadIdx.x / S::TPF, tid = threadIdx.x % S::TPF;     // slots 0..15: rows, 16..31: mirrors
-	float2 *buf = smem + slot * S::BUF;
+	float2 *buf = smem + slot * slot_stride<LOG2M2>();
 	const int m1 = 1 << log2m1;
 	const int tiles = m1 / (2 * LG_CB) + 1;                // k1 tiles 0, 16, ..., m1/2
 	const int64_t fb = blockIdx.x / tiles;
@@ -130,15 +137,20 @@ stft_large_rows_kernel(StftArgs a, int log2m1, int64_t batch0, const float2 *__r
 	stockham_pass_slot<LOG2M2, 0, false>(tid, ld, buf, tw2t, sync);
 	RunPassesSlot<LOG2M2, false, 1, BlockSync>::run(tid, buf, tw2t, sync);
 	__syncthreads();
-	if (slot >= LG_CB || k1s > m1 / 2) return;
-	// X[k], k = k1s + m1*k2, pairs with X[M-k] = mirror row, column m2-1-k2 (row 0: m2-k2, wrapping)
+	// Epilogue with 16 consecutive lanes on 16 adjacent rows k1: bins k = k1 + m1*k2 of one k2 are
+	// contiguous in the output, so every 16-lane group writes a 128-byte run (and its mirror run).
+	// X[k] pairs with X[M-k] = mirror row, column m2-1-k2 (row 0: m2-k2, wrapping).
+	const int r = threadIdx.x & (LG_CB - 1);
+	const int k1e = k1_0 + r;
+	if (k1e > m1 / 2) return;
 	const int64_t M = (int64_t)1 << (LOG2M2 + log2m1);
-	const float2 *mir = smem + (slot + LG_CB) * S::BUF;
+	const float2 *own = smem + r * slot_stride<LOG2M2>();
+	const float2 *mir = smem + (r + LG_CB) * slot_stride<LOG2M2>();
 	const int64_t row = ch * a.out_ch_stride + t * a.out_pitch;
-	for (int k2 = tid; k2 < S::M; k2 += S::TPF) {
-		const int64_t k = k1s + ((int64_t)k2 << log2m1);
-		const int k2m = k1s == 0 ? ((S::M - k2) & (S::M - 1)) : (S::M - 1 - k2);
-		const float2 zk = buf[pad16(k2)];
+	for (int k2 = threadIdx.x / LG_CB; k2 < S::M; k2 += 2 * S::TPF) {
+		const int64_t k = k1e + ((int64_t)k2 << log2m1);
+		const int k2m = k1e == 0 ? ((S::M - k2) & (S::M - 1)) : (S::M - 1 - k2);
+		const float2 zk = own[pad16(k2)];
 		const float2 zm = mir[pad16(k2m)];
 		const float2 w = tw2(lt.s_lo, lt.s_hi, (int)k);
 		const float ex = zk.x + zm.x, ey = zk.y - zm.y;
@@ -163,7 +175,7 @@ static int launch_cols(const StftArgs &a, int log2m2, int64_t batch0, int64_t nb
                        const LargeTables &lt, float2 *scratch, cudaStream_t st) {
 	using S = FftSched<LOG2M1>;
 	auto kern = stft_large_cols_kernel<LOG2M1>;
-	const int smem = LG_CB * S::BUF * (int)sizeof(float2);
+	const int smem = LG_CB * slot_stride<LOG2M1>() * (int)sizeof(float2);
 	PAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 	const int64_t grid = nb * ((1 << log2m2) / LG_CB);
 	kern<<<(unsigned)grid, LG_CB * S::TPF, smem, st>>>(a, log2m2, batch0, tw1, lt, scratch);
@@ -177,7 +189,7 @@ static int launch_rows(const StftArgs &a, int log2m1, int64_t batch0, int64_t nb
                        const LargeTables &lt, const float2 *scratch, cudaStream_t st) {
 	using S = FftSched<LOG2M2>;
 	auto kern = stft_large_rows_kernel<LOG2M2, MAG>;
-	const int smem = 2 * LG_CB * S::BUF * (int)sizeof(float2);
+	const int smem = 2 * LG_CB * slot_stride<LOG2M2>() * (int)sizeof(float2);
 	PAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 	const int64_t grid = nb * ((1 << log2m1) / (2 * LG_CB) + 1);
 	const float half_scale = (float)(0.5 / sqrt((double)a.n_fft));
