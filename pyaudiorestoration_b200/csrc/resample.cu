@@ -521,8 +521,16 @@ sinc_kernel(SincArgs a, const float *__restrict__ ctab, const float *__restrict_
 		if (live && su.cnt > 0) {
 			if (staged && interior) {
 				const float *xrow = xs + (int)(su.lower - tlo) * CH;
+#if defined(SINC_EXPERIMENT_SKIP_TAPS)          // development aid (scripts/try_variants.sh): fixed cost only
+				acc[0] = xrow[0] * su.s + (float)su.f_fx;
+#elif defined(SINC_EXPERIMENT_ALL_FC1)
+				taps_fast<CH, false>(su, nt, nblk, ctab_s, xrow, acc);
+#elif defined(SINC_EXPERIMENT_ALL_LOWPASS)
+				taps_fast<CH, true>(su, nt, nblk, hptab_s, xrow, acc);
+#else
 				if (su.lowpass) taps_fast<CH, true>(su, nt, nblk, hptab_s, xrow, acc);
 				else taps_fast<CH, false>(su, nt, nblk, ctab_s, xrow, acc);
+#endif
 			} else {
 				// first / last NT outputs of a file, or a span too wide for shared memory
 #pragma unroll
