@@ -10,9 +10,10 @@ samples processed per second over all GPUs.
 
   value      device-resident: inputs already in HBM, outputs left in HBM, timed with CUDA events on
              the launch stream, barrier + synchronize on both sides, max over ranks.
-  e2e        the same step through the reference-facing Python API (util.fourier.stft per channel,
-             util.resampling.speed_to_pos + resample_channels = the body of run()), numpy in ->
-             numpy out: every step copies its inputs host->device and its results device->host.
+  e2e        the same step through the reference-facing Python API: util.fourier.stft(sig[:, c]) per
+             channel (as the GUIs call it) + util.resampling.varispeed (= run() minus the WAV write) on
+             an interleaved pinned (frames, channels) float32 array, numpy arrays out: every step copies
+             its inputs host->device and its results device->host.
   roofline   the dominant kernel (the sinc interpolator), algorithmic bytes / CUDA-event time,
              against MEASURED_PEAKS.json; roofline_stft / roofline_positions give the other two.
   cpu_baseline  the CPU oracle (port of the reference's numpy/numba path) on a bounded sample.
@@ -508,8 +509,11 @@ def main():
                              {"note": "sinc stage is FP32-issue/MUFU bound (2*NT reciprocals per output sample), "
                                       "not HBM bound; see DESIGN.md",
                               "taps_per_s": C * m * 2 * NT / (k_sinc * 1e-3)}),
-            "roofline_stft": roof(bytes_stft, k_stft, "stft_kernel"),
-            "roofline_positions": roof(bytes_pos, k_pos, "expand_positions_kernel"),
+            "roofline_stft": roof(bytes_stft, k_stft, "stft_kernel",
+                                  {"note": "stft_tma_kernel<11,0>: TMA-staged frames, HBM-bound by design"}),
+            "roofline_positions": roof(bytes_pos, k_pos, "expand_positions_kernel",
+                                       {"note": "stage time includes the serial host chain of speed_to_pos (2 stream "
+                                                "synchronisations); kernels: expand_positions + add_offsets"}),
             "stage_ms": {"stft": k_stft, "positions": k_pos, "sinc": k_sinc},
             "cpu_baseline": cpu,
         }
