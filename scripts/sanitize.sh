@@ -1,0 +1,10 @@
+#!/bin/bash
+# compute-sanitizer passes over a small slice of the GPU parity tests (the reference has
+# no race detection; this is ours).  memcheck: out-of-bounds / misaligned accesses; racecheck: shared-memory
+# hazards in the slot-barrier STFT, the tiled resampler and the positions tile transpose.
+SEL="test_stft_golden_cases or test_stft_zeropad or test_istft_golden or test_sinc_golden or test_speed_to_pos_golden_bit_exact or test_linear_mode or test_varispeed_capacity_error or test_stft_large_zeropad_and_multichannel or test_time_shards"
+for tool in memcheck racecheck; do
+  compute-sanitizer --tool $tool --error-exitcode 7 --print-limit 5 python -m pytest tests -m gpu -q -x --timeout 1500 -k "$SEL" \
+      > gpurun_out/sanitizer_$tool.log 2>&1
+  echo "$tool exit=$? : $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|passed|failed' gpurun_out/sanitizer_$tool.log | tail -3 | tr '\n' ' ')"
+done
