@@ -149,6 +149,24 @@ PAR_API int par_varispeed_f32(const double *sampletimes, const double *speeds, i
                       int mode, int nt, float *out, int64_t out_cap, int64_t out_stride, int64_t out_ch_stride,
                       int64_t *m, unsigned flags, int device, void *stream);
 
+/* ---- frequency trackers on the magnitude spectrogram: util/wow_detection.py:119-139 (get_peak),
+ *      :294-302 (PeakTracker), :305-327 (PeakTrackTracker), :256-291 (CenterOfGravity) ------------
+ * mag: float32 magnitudes as par_stft_f32 writes them (frame t at t*pitch, bins contiguous; host, or
+ * device with PAR_DEVICE_PTRS).  freqs: HOST float64[count]; in: the drawn trail sampled at frames
+ * frame0 .. frame0+count-1 (Track.sample_trail, :66-76), out: the traced frequency per frame.
+ * fft_size is the transform length (n_fft*zeropad), tolerance_st the band half-width in semitones. */
+#define PAR_TRACE_PEAK 0
+#define PAR_TRACE_PEAK_TRACK 1
+#define PAR_TRACE_COG 2
+PAR_API int par_trace_f32(const float *mag, int num_bins, int64_t n_frames, int64_t pitch, int64_t frame0,
+                  int64_t count, int fft_size, double sr, double tolerance_st, int mode, double *freqs,
+                  unsigned flags, int device, void *stream);
+/* Fused: the magnitudes of frames [frame0, frame0+count) of the transform of x are computed on the
+ * device, traced there and discarded; only `count` doubles come back (x host or device as usual). */
+PAR_API int par_stft_trace_f32(const float *x, int64_t n, int64_t x_stride, int n_fft, int hop, int zeropad,
+                       const float *window, int64_t frame0, int64_t count, double sr, double tolerance_st,
+                       int mode, double *freqs, unsigned flags, int device, void *stream);
+
 /* ---- time-sharded jobs: one rank's slice of a long signal --------------------
  * Device pointers only (PAR_DEVICE_PTRS must be set).  Indices are GLOBAL sample / frame / output
  * numbers; the rank passes the slice it holds and where that slice starts.

@@ -367,3 +367,81 @@ def heuristic_peaks_ref(magnitude, sr, fft_size, f_lower, f_upper, num_bands):
         peaks, _ = scipy.signal.find_peaks(-vol, prominence=5, rel_height=0.5)
         out.append(peaks)
     return out
+
+
+# --------------------------------------------------------------------------- frequency trackers (8f rank 1)
+
+def _track_setup(spectrum, trail, fft_size, hop, sr):
+    """Track.__init__ / sample_trail / ensure_frames -- util/wow_detection.py:32-89."""
+    num_bins, frame_1 = spectrum.shape
+    trail = sorted(trail, key=lambda tup: tup[0])
+    times_raw = [d[0] for d in trail]
+    freqs_raw = [d[1] for d in trail]
+    frame_0 = 0
+    if times_raw[0]:
+        frame_0 = max(frame_0, int(times_raw[0] * sr / hop))
+    if times_raw[-1]:
+        frame_1 = min(frame_1, int(times_raw[-1] * sr / hop))
+    times = np.linspace(frame_0 * hop / sr, frame_1 * hop / sr, frame_1 - frame_0)
+    freqs = np.interp(times, times_raw, freqs_raw)
+    return num_bins, frame_0, times, freqs
+
+
+def _bin_limits(freq, tolerance, num_bins, fft_size, sr, min_bins=4):
+    """freq_plus_tolerance :106-116 + set_bin_limits :91-104 + freq_2_bin :79-80."""
+    logfreq = np.log2(freq)
+    fl = max(1.0, np.power(2, (logfreq - tolerance)))
+    fu = min(sr / 2, np.power(2, (logfreq + tolerance)))
+
+    def f2b(f):
+        return max(1, min(num_bins - 1, int(round(f * fft_size / sr))))
+    nl, nu = f2b(fl), f2b(fu)
+    while (nu - nl) < min_bins:
+        nl -= 1
+        nu += 1
+    return nl, nu
+
+
+def _get_peak(spectrum, frame, nl, nu, fft_size, sr):
+    """get_peak :119-134 (rectangular window) + is_peak :136-139 + parabolic (util/correlation.py:42-46)."""
+    fft_frame = spectrum[:, frame]
+    peak = nl + np.argmax(fft_frame[nl:nu] * np.ones(nu - nl))
+    if fft_frame[peak - 1] < fft_frame[peak] > fft_frame[peak + 1]:
+        f = fft_frame
+        peak = 1 / 2. * (f[peak - 1] - f[peak + 1]) / (f[peak - 1] - 2 * f[peak] + f[peak + 1]) + peak
+    return peak / fft_size * sr
+
+
+def _interp_nans(y):
+    nans = np.isnan(y)
+    if nans.any() and (~nans).any():
+        y[nans] = np.interp(nans.nonzero()[0], (~nans).nonzero()[0], y[~nans])
+    return y
+
+
+def track_ref(mode, spectrum, trail, fft_size, hop, sr, tolerance_st=1):
+    """``(times, freqs)`` of PeakTracker.trace (:294-302, mode 'peak'), PeakTrackTracker.trace (:305-327,
+    'peak_track') or CenterOfGravity.trace (:256-291, 'cog') on a (bins, frames) magnitude array."""
+    spectrum = np.asarray(spectrum)
+    num_bins, frame_0, times, freqs = _track_setup(spectrum, trail, fft_size, hop, sr)
+    tol = tolerance_st / 12
+    if mode == "peak":
+        for i, raw in enumerate(freqs):
+            nl, nu = _bin_limits(raw, tol, num_bins, fft_size, sr)
+            freqs[i] = _get_peak(spectrum, frame_0 + i, nl, nu, fft_size, sr)
+    elif mode == "peak_track":
+        freq = freqs[0]
+        for i in range(len(freqs)):
+            nl, nu = _bin_limits(freq, tol / 2 if i > 2 else tol, num_bins, fft_size, sr)
+            freqs[i] = _get_peak(spectrum, frame_0 + i, nl, nu, fft_size, sr)
+    elif mode == "cog":
+        fft_freqs = np.arange(0, (fft_size // 2 + 1)) / float(fft_size) * float(sr)
+        nl, nu = _bin_limits(freqs[0], tol, num_bins, fft_size, sr)
+        for i in range(len(freqs)):
+            weighted = np.hanning(nu - nl) * spectrum[nl:nu, frame_0 + i]
+            with np.errstate(divide="ignore", invalid="ignore"):
+                freqs[i] = 2 ** (np.sum(weighted * np.log2(fft_freqs[nl:nu])) / np.sum(weighted))
+            nl, nu = _bin_limits(freqs[i], tol, num_bins, fft_size, sr)
+    else:
+        raise ValueError(mode)
+    return times, _interp_nans(freqs)

@@ -574,14 +574,16 @@ PAR_API int par_istft_f32(const void *S, int n_fft, int64_t n_frames, int64_t s_
 PAR_API int par_speed_segments(const double *sampletimes, const double *speeds, int64_t k,
                        int64_t *seg_n, int64_t *total) {
 	if (!sampletimes || !speeds || k < 2 || !seg_n) { set_error("speed_segments: bad argument"); return PAR_EINVAL; }
-	// util/resampling.py:111-118; this translation unit is compiled with -ffp-contract=off
-	volatile double err = 0.0;
+	// util/resampling.py:111-118.  Host code of this file is compiled with -ffp-contract=off and x86-64
+	// doubles are IEEE (SSE2), so every statement below is one correctly rounded operation, in the
+	// reference's order: periods[i] * mean(speeds[i:i+2]) + err.
+	double err = 0.0;
 	int64_t sum = 0;
 	for (int64_t i = 0; i + 1 < k; i++) {
-		volatile double period = sampletimes[i + 1] - sampletimes[i];
-		volatile double mean = (speeds[i] + speeds[i + 1]) / 2.0;
-		volatile double prod = period * mean;
-		volatile double inerr = prod + err;
+		const double period = sampletimes[i + 1] - sampletimes[i];
+		const double mean = (speeds[i] + speeds[i + 1]) / 2.0;
+		const double prod = period * mean;
+		const double inerr = prod + err;
 		const double nr = nearbyint(inerr);       // Python round(): half to even
 		if (!(fabs(nr) < 9.0e15)) { set_error("speed_segments: non-finite segment length"); return PAR_EINVAL; }
 		const int64_t n = (int64_t)nr;
@@ -637,36 +639,38 @@ static int positions_device(const double *sampletimes, const double *speeds, int
 	PAR_CUDA(cudaMemcpyAsync(sums.data(), d_sum.p, n_seg * sizeof(double), cudaMemcpyDeviceToHost, st));
 	PAR_CUDA(cudaStreamSynchronize(st));
 
-	// serial offset chain + end test (util/resampling.py:125-135)
-	volatile double offset = sampletimes[0];
+	// serial offset chain + end test (util/resampling.py:125-135): one addition per segment; the
+	// division for the block's first position is only needed once the end test can fire
+	double offset = sampletimes[0];
 	int64_t m = total;
 	for (int64_t i = 0; i < n_seg; i++) {
 		off[i] = offset;
 		const int64_t n = seg_n[i];
 		if (n <= 0) continue;                   // the reference raises on an empty block
-		volatile double inv0 = 1.0 / speeds[i];
-		if (n == 1) inv0 = NAN;                 // arange(1)/0 -> nan in the reference
-		volatile double first = inv0 + offset;
-		volatile double last = sums[i] + offset;
-		if (first <= num_input_samples && num_input_samples <= last) {
-			// np.argmin(|sample_at - L|) over this block, first minimum
-			const double ds = speeds[i + 1] - speeds[i];
-			const double nm1 = (double)(n - 1);
-			volatile double acc = 0.0;
-			double best = INFINITY;
-			int64_t besti = 0;
-			for (int64_t j = 0; j < n; j++) {
-				volatile double q = (double)j / nm1;
-				volatile double v = q * ds;
-				v = v + speeds[i];
-				volatile double r = 1.0 / v;
-				acc = acc + r;
-				volatile double pj = acc + offset;
-				const double dist = fabs(pj - num_input_samples);
-				if (dist < best) { best = dist; besti = j; }
+		const double last = sums[i] + offset;
+		if (num_input_samples <= last) {
+			double inv0 = 1.0 / speeds[i];
+			if (n == 1) inv0 = NAN;               // arange(1)/0 -> nan in the reference
+			const double first = inv0 + offset;
+			if (first <= num_input_samples) {
+				// np.argmin(|sample_at - L|) over this block, first minimum
+				const double ds = speeds[i + 1] - speeds[i];
+				const double nm1 = (double)(n - 1);
+				double acc = 0.0, best = INFINITY;
+				int64_t besti = 0;
+				for (int64_t j = 0; j < n; j++) {
+					const double q = (double)j / nm1;
+					double v = q * ds;
+					v = v + speeds[i];
+					const double r = 1.0 / v;
+					acc = acc + r;
+					const double pj = acc + offset;
+					const double dist = fabs(pj - num_input_samples);
+					if (dist < best) { best = dist; besti = j; }
+				}
+				m = seg_start[i] + besti;
+				break;
 			}
-			m = seg_start[i] + besti;
-			break;
 		}
 		offset = last;
 	}
@@ -901,6 +905,95 @@ PAR_API int par_varispeed_f32(const double *sampletimes, const double *speeds, i
 	if (*m == 0) return PAR_OK;
 	return resample_with_dev_pos(sinc, dpos.as<double>(), *m, signal, n_in, sig_stride, n_ch, sig_ch_stride, nt, out,
 	                             out_stride, out_ch_stride, flags, device, st, &chain, monotone);
+}
+
+// ---- trackers ----------------------------------------------------------------------------------
+static int trace_on_device(const float *mag_dev, int64_t pitch, int num_bins, int64_t frame0, int64_t count,
+                           int fft_size, double sr, double tolerance_st, int mode, double *freqs, cudaStream_t st) {
+	int rc;
+	DevBuf df(st);
+	if ((rc = df.alloc((size_t)count * sizeof(double))) != PAR_OK) return rc;
+	PAR_CUDA(cudaMemcpyAsync(df.p, freqs, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, st));
+	rc = launch_trace(mag_dev, pitch, num_bins, frame0, count, fft_size, sr, tolerance_st / 12.0, mode, freqs[0],
+	                  df.as<double>(), st);
+	if (rc != PAR_OK) return rc;
+	PAR_CUDA(cudaMemcpyAsync(freqs, df.p, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, st));
+	PAR_CUDA(cudaStreamSynchronize(st));
+	return PAR_OK;
+}
+
+static int check_trace_args(int num_bins, int64_t n_frames, int64_t frame0, int64_t count, int fft_size, double sr,
+                            double tolerance_st, int mode, const double *freqs) {
+	if (num_bins < 8 || frame0 < 0 || count < 0 || frame0 + count > n_frames || fft_size < 2 || !(sr > 0) ||
+	    !(tolerance_st >= 0) || mode < PAR_TRACE_PEAK || mode > PAR_TRACE_COG || (count > 0 && !freqs)) {
+		set_error("trace: bad argument");
+		return PAR_EINVAL;
+	}
+	for (int64_t i = 0; i < count; i++)
+		if (!(freqs[i] > 0.0) || !(freqs[i] < 1e12)) { set_error("trace: trail frequencies must be positive"); return PAR_EINVAL; }
+	return PAR_OK;
+}
+
+PAR_API int par_trace_f32(const float *mag, int num_bins, int64_t n_frames, int64_t pitch, int64_t frame0,
+                  int64_t count, int fft_size, double sr, double tolerance_st, int mode, double *freqs,
+                  unsigned flags, int device, void *stream) {
+	if (!mag || pitch < num_bins) { set_error("trace: bad spectrogram"); return PAR_EINVAL; }
+	int rc = check_trace_args(num_bins, n_frames, frame0, count, fft_size, sr, tolerance_st, mode, freqs);
+	if (rc != PAR_OK) return rc;
+	if ((rc = use_device(device)) != PAR_OK) return rc;
+	if (count == 0) return PAR_OK;
+	cudaStream_t st = (cudaStream_t)stream;
+	if (flags & PAR_DEVICE_PTRS)
+		return trace_on_device(mag, pitch, num_bins, frame0, count, fft_size, sr, tolerance_st, mode, freqs, st);
+	DevBuf dm(st);                                       // only the traced frames are uploaded
+	if ((rc = dm.alloc((size_t)count * pitch * sizeof(float))) != PAR_OK) return rc;
+	PAR_CUDA(cudaMemcpyAsync(dm.p, mag + frame0 * pitch, (size_t)count * pitch * sizeof(float), cudaMemcpyHostToDevice, st));
+	return trace_on_device(dm.as<float>(), pitch, num_bins, 0, count, fft_size, sr, tolerance_st, mode, freqs, st);
+}
+
+PAR_API int par_stft_trace_f32(const float *x, int64_t n, int64_t x_stride, int n_fft, int hop, int zeropad,
+                       const float *window, int64_t frame0, int64_t count, double sr, double tolerance_st,
+                       int mode, double *freqs, unsigned flags, int device, void *stream) {
+	if (!x || !window || n < 1 || n_fft < 2 || hop < 1 || zeropad < 1 || x_stride < 1) {
+		set_error("stft_trace: bad argument");
+		return PAR_EINVAL;
+	}
+	const int64_t T = par_stft_num_frames(n, n_fft, hop);
+	const int num_bins = (int)((int64_t)n_fft * zeropad / 2 + 1);
+	int rc = check_trace_args(num_bins, T, frame0, count, n_fft * zeropad, sr, tolerance_st, mode, freqs);
+	if (rc != PAR_OK) return rc;
+	if ((rc = use_device(device)) != PAR_OK) return rc;
+	if (count == 0) return PAR_OK;
+	cudaStream_t st = (cudaStream_t)stream;
+	const float *dwin = device_window(device, window, n_fft, st);
+	if (!dwin) return PAR_ECUDA;
+	DevBuf dmag(st), dplanar(st);
+	AudioUploader up(st);
+	if ((rc = dmag.alloc((size_t)count * num_bins * sizeof(float))) != PAR_OK) return rc;
+	StftArgs a;
+	a.n = n; a.n_ch = 1; a.n_fft = n_fft; a.hop = hop; a.zeropad = zeropad; a.window = dwin; a.magnitude = 1;
+	a.frame0 = frame0; a.n_frames = count; a.x_origin = 0; a.x_ch_stride = 0;
+	if (flags & PAR_DEVICE_PTRS) {
+		a.x = x; a.x_stride = x_stride;
+	} else {
+		if ((rc = up.init(x, n, x_stride, 1, 0)) != PAR_OK) return rc;
+		if ((rc = up.upload_to(n, st)) != PAR_OK) return rc;
+		const DevAudio da = up.view();
+		if (da.stride != 1) {
+			if ((rc = dplanar.alloc((size_t)up.n_al * sizeof(float))) != PAR_OK) return rc;
+			if ((rc = launch_deinterleave(da.p, n, da.stride, 1, da.ch_stride, dplanar.as<float>(), up.n_al, device, st)) != PAR_OK)
+				return rc;
+			a.x = dplanar.as<float>();
+		} else {
+			a.x = da.p;
+		}
+		a.x_stride = 1;
+	}
+	// row 0 of the scratch spectrogram is frame frame0
+	a.out = (char *)dmag.p - (size_t)frame0 * num_bins * sizeof(float);
+	a.out_pitch = num_bins; a.out_ch_stride = 0;
+	if ((rc = launch_stft(a, device, st)) != PAR_OK) return rc;
+	return trace_on_device(dmag.as<float>(), num_bins, num_bins, 0, count, n_fft * zeropad, sr, tolerance_st, mode, freqs, st);
 }
 
 // ---- shard entry points (device pointers only): one rank's slice of a time-sharded job ----------

@@ -87,6 +87,9 @@ struct SincArgs {
 };
 int launch_sinc(const SincArgs &a, int device, cudaStream_t st);
 int launch_linear(const SincArgs &a, int device, cudaStream_t st);
+int launch_trace(const float *mag_dev, int64_t pitch, int num_bins, int64_t frame0, int64_t count, int fft_size,
+                 double sr, double tolerance_octaves, int mode, double first_freq, double *freqs_dev,
+                 cudaStream_t st);
 // dst[c * dst_ch_stride + i] = src[i * stride + c * ch_stride]
 int launch_deinterleave(const float *src, int64_t n, int64_t stride, int n_ch, int64_t ch_stride, float *dst,
                         int64_t dst_ch_stride, int device, cudaStream_t st);

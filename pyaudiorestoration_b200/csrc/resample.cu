@@ -453,7 +453,7 @@ __device__ __forceinline__ float taps_slow(const SampleSetup &su, int nt, const 
 }
 
 template <int CH>
-__global__ void __launch_bounds__(SINC_TILE, SINC_MIN_BLOCKS)
+__global__ void __launch_bounds__(SINC_TILE, CH >= 8 ? 2 : SINC_MIN_BLOCKS)
 sinc_kernel(SincArgs a, const float *__restrict__ ctab, const float *__restrict__ hptab, int nblk, int span_cap) {
 	extern __shared__ __align__(16) float smem_f[];
 	// [c table | hp table] (16 * (nblk + 1) floats each), then the staged samples:
@@ -581,6 +581,8 @@ int launch_sinc(const SincArgs &a, int device, cudaStream_t st) {
 	SincTables tb;
 	int rc = sinc_tables(device, a.nt, st, &tb);
 	if (rc != PAR_OK) return rc;
+	// the tap weights of an output sample are computed once per channel group: widest group that fits
+	if (a.n_ch >= 8) return launch_sinc_ch<8>(a, device, st, tb);
 	if (a.n_ch >= 4) return launch_sinc_ch<4>(a, device, st, tb);
 	if (a.n_ch >= 2) return launch_sinc_ch<2>(a, device, st, tb);
 	return launch_sinc_ch<1>(a, device, st, tb);

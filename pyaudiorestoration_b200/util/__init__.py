@@ -3,7 +3,7 @@
 CPU-only import of one of them does not pull the other."""
 import importlib
 
-__all__ = ["fourier", "resampling", "io_ops", "timing"]
+__all__ = ["fourier", "resampling", "io_ops", "timing", "flac", "wow_detection"]
 
 
 def __getattr__(name):

@@ -649,3 +649,68 @@ def test_cfg4_max_mono(fourier):
     for k in ("max", "min"):
         # a cell flips channel only if |L| and |R| agree to float32 rounding; allow a handful of such cells
         assert rel_l2(got[k].astype(np.float64), want[k].astype(np.float64)) <= 5e-6
+
+
+# ----------------------------------------------------------------------------------------- trackers (8f rank 1)
+def _wow_signal(sr=44100, dur=3.0, seed=5):
+    rng = np.random.default_rng(seed)
+    t = np.arange(int(sr * dur)) / sr
+    inst = 3150.0 * (1 + 0.006 * np.sin(2 * np.pi * 0.8 * t))
+    phase = 2 * np.pi * np.cumsum(inst) / sr
+    x = 0.3 * np.sin(phase) + 0.05 * np.sin(2.31 * phase) + 0.01 * rng.standard_normal(len(t))
+    return x.astype(np.float32), sr
+
+
+def test_trackers_match_reference_classes(golden_dir, fourier):
+    """Device trackers vs (a) the oracle on the very same GPU magnitudes: Peak / Peak Track identical
+    (index work + fixed float32/float64 op sequence), Center of Gravity to 1e-9; (b) the golden output
+    of the unmodified reference classes on CPU magnitudes: same trace within the spectrogram's 1e-6."""
+    from pyaudiorestoration_b200.util import wow_detection
+    z = _load(golden_dir, "trackers")
+    x, sr = _wow_signal()
+    fft_size, hop, sr2, zp = (int(v) for v in z["params"])
+    assert sr == sr2
+    trail = [tuple(r) for r in z["trail"]]
+    mag = fourier.get_mag(x, fft_size, hop, "blackmanharris", zp)
+    for key, name in (("peak", "Peak"), ("peak_track", "Peak Track"), ("cog", "Center of Gravity")):
+        tr = wow_detection.wow_detectors[name](mag, x, list(trail), fft_size * zp, hop, sr, 1.0, "Linear")
+        t_ref, f_ref = onp.track_ref(key, np.array(mag), trail, fft_size * zp, hop, sr, 1.0)
+        assert np.array_equal(tr.times, t_ref) and np.array_equal(tr.times, z[key + "__times"])
+        if key == "cog":
+            assert np.max(np.abs(tr.freqs - f_ref) / f_ref) <= 1e-9
+        else:
+            assert np.array_equal(tr.freqs, f_ref), key
+        assert np.max(np.abs(tr.freqs - z[key + "__freqs"]) / z[key + "__freqs"]) <= 2e-6, key
+        # fused: spectrogram never materialised
+        t2, f2 = wow_detection.trace_signal(x, trail, fft_size, hop, sr, name, 1.0, "blackmanharris", zp)
+        assert np.array_equal(t2, tr.times) and np.array_equal(f2, tr.freqs), key
+    # the trace follows the synthetic wow: +-0.6 % around 3150 Hz at 0.8 Hz
+    assert 10 < np.std(tr.freqs) < 16
+
+
+def test_trackers_on_strided_signal_and_host_copy(fourier):
+    from pyaudiorestoration_b200.util import wow_detection
+    x, sr = _wow_signal(dur=2.0, seed=9)
+    stereo = np.stack([x, x[::-1]], axis=1)
+    trail = [(0.2, 3150.0), (1.8, 3150.0)]
+    t1, f1 = wow_detection.trace_signal(stereo[:, 0], trail, 2048, 128, sr, "Peak", 2.0)
+    mag = np.array(fourier.get_mag(stereo[:, 0], 2048, 128))            # an ordinary (bins, frames) C array
+    tr = wow_detection.PeakTracker(mag, None, trail, 2048, 128, sr, 2.0)
+    assert np.array_equal(t1, tr.times) and np.array_equal(f1, tr.freqs)
+    assert abs(np.mean(f1) - 3150.0) < 5.0
+
+
+@pytest.mark.parametrize("channels", [3, 4, 8, 9])
+def test_sinc_channel_groups(resampling, channels):
+    """Channel groups of 8 / 4 / 2 / 1 share one set of tap weights per output sample; every channel
+    must equal the single-channel result bit for bit."""
+    sr = 48000
+    sig = np.stack([synth(sr, 200 + c, sr) for c in range(channels)], axis=1)
+    curve = wow_curve(1.0, sr, 512, depth=0.04, freq=2.5)
+    out = resampling.varispeed(sig, sr, curve, None, "Sinc", 64)
+    pos = oracle.speed_to_pos_c(curve[:, 0] * sr, curve[:, 1], len(sig))
+    assert out.shape == (len(pos), channels)
+    for c in (0, channels // 2, channels - 1):
+        single = resampling.sinc_wrapper(pos, sig[:, c], 0, 64)
+        assert np.array_equal(out[:, c], single), c
+    _check_sinc(np.ascontiguousarray(out[:, channels - 1]), pos, np.ascontiguousarray(sig[:, channels - 1]), 64)

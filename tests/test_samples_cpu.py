@@ -73,3 +73,21 @@ def test_cfg4_oracle_heal_matches_reference_bitwise(golden_dir):
     from pyaudiorestoration_b200 import dropouts
     regs = [dropouts.marker_region(dropouts.Dropout(*m), sr, fft_size, hop) for m in z["markers"].tolist()]
     assert np.array_equal(np.array(regs), z["regions"])
+
+
+def test_tracker_oracle_matches_reference_classes_bitwise(golden_dir):
+    """the oracle's restatement of PeakTracker / PeakTrackTracker / CenterOfGravity
+    against tests/golden/trackers.npz (the unmodified reference classes, make_golden_trackers.py)."""
+    z = np.load(os.path.join(golden_dir, "trackers.npz"))
+    rng = np.random.default_rng(5)
+    sr, dur = 44100, 3.0
+    t = np.arange(int(sr * dur)) / sr
+    phase = 2 * np.pi * np.cumsum(3150.0 * (1 + 0.006 * np.sin(2 * np.pi * 0.8 * t))) / sr
+    x = (0.3 * np.sin(phase) + 0.05 * np.sin(2.31 * phase) + 0.01 * rng.standard_normal(len(t))).astype(np.float32)
+    fft_size, hop, sr2, zp = (int(v) for v in z["params"])
+    spec = onp.to_mag(onp.stft_ref(x, fft_size, hop)).astype(np.float32)
+    assert float(spec.astype(np.float64).sum()) == z["spec_checksum"][0]
+    trail = [tuple(r) for r in z["trail"]]
+    for mode in ("peak", "peak_track", "cog"):
+        times, freqs = onp.track_ref(mode, spec, trail, fft_size, hop, sr)
+        assert np.array_equal(times, z[mode + "__times"]) and np.array_equal(freqs, z[mode + "__freqs"]), mode
