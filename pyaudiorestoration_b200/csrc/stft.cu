@@ -360,8 +360,6 @@ static int launch_one(const StftArgs &a, int device, cudaStream_t st) {
 	const float2 *tw = fft_twiddles(device, LOG2M, st);
 	if (!tw) return PAR_ECUDA;
 	auto kern = stft_kernel<LOG2M, MAG>;
-	static thread_local int configured_dev[64] = {0};
-	(void)configured_dev;
 	PAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
 	int occ = 0;
 	PAR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::BLOCK, C::SMEM));

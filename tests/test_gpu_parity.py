@@ -714,3 +714,39 @@ def test_sinc_channel_groups(resampling, channels):
         single = resampling.sinc_wrapper(pos, sig[:, c], 0, 64)
         assert np.array_equal(out[:, c], single), c
     _check_sinc(np.ascontiguousarray(out[:, channels - 1]), pos, np.ascontiguousarray(sig[:, channels - 1]), 64)
+
+
+# ----------------------------------------------------------------------------------------- re-entrancy
+def test_concurrent_calls_from_threads(fourier, resampling):
+    """The reference enters this path from QThread workers while the GUI thread calls stft/istft
+    (util/qt_threads.py:19-35): concurrent calls from several host threads must give exactly the
+    results of the same calls made one after the other."""
+    import threading
+    sr = 48000
+    sigs = [np.stack([synth(sr * 2, 300 + 2 * k, sr), synth(sr * 2, 301 + 2 * k, sr)], axis=1) for k in range(4)]
+    curve = wow_curve(2.0, sr, 512, depth=0.02, freq=1.1)
+
+    def work(k):
+        s = fourier.stft(sigs[k][:, 0], 2048, 512)
+        m = fourier.get_mag(sigs[k][:, 1], 1024, 128, "hann", 2)
+        y = resampling.varispeed(sigs[k], sr, curve, None, "Sinc", 32)
+        r = fourier.istft(s, hop_length=512, length=sr * 2)
+        return [np.array(v) for v in (s, m, y, r)]
+    serial = [work(k) for k in range(4)]
+    results, errors = [None] * 4, []
+
+    def runner(k):
+        try:
+            for _ in range(3):
+                results[k] = work(k)
+        except Exception as e:                      # noqa: BLE001
+            errors.append(e)
+    threads = [threading.Thread(target=runner, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for k in range(4):
+        for a, b in zip(results[k], serial[k]):
+            assert np.array_equal(a, b)
