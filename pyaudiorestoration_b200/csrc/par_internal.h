@@ -47,6 +47,7 @@ struct StftArgs {
 	int magnitude;
 };
 int launch_stft(const StftArgs &a, int device, cudaStream_t st);
+int launch_stft_mid(const StftArgs &a, int log2m, int device, cudaStream_t st);     // log2m in {13, 14}
 int launch_stft_large(const StftArgs &a, int log2m, int device, cudaStream_t st);   // 15 <= log2m <= 19
 
 struct IstftArgs {

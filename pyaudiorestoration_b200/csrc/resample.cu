@@ -16,6 +16,8 @@
 //     fixed point (fc needs more than float32 precision: its error is multiplied by up to NT).
 // Positions, the rounding to the nearest input sample, the fractional shift and fc are
 // float64 like the reference; the tap loop is float32 (parity bound 1e-6, see tests).
+#include <stdlib.h>
+
 #include "par_internal.h"
 #include "../../include/par_b200.h"
 
@@ -581,8 +583,12 @@ int launch_sinc(const SincArgs &a, int device, cudaStream_t st) {
 	SincTables tb;
 	int rc = sinc_tables(device, a.nt, st, &tb);
 	if (rc != PAR_OK) return rc;
-	// the tap weights of an output sample are computed once per channel group: widest group that fits
-	if (a.n_ch >= 8) return launch_sinc_ch<8>(a, device, st, tb);
+	// The tap weights of an output sample are computed once per channel group.  Groups of 4 are the
+	// sweet spot: a group of 8 needs 128 registers (2 CTAs/SM) and is shared-memory-bandwidth bound
+	// just like two groups of 4 -- measured 25 % slower on the 8-channel config ($PAR_B200_SINC_CH8=1
+	// selects it for experiments).
+	static const bool ch8 = getenv("PAR_B200_SINC_CH8") && atoi(getenv("PAR_B200_SINC_CH8")) > 0;
+	if (ch8 && a.n_ch >= 8) return launch_sinc_ch<8>(a, device, st, tb);
 	if (a.n_ch >= 4) return launch_sinc_ch<4>(a, device, st, tb);
 	if (a.n_ch >= 2) return launch_sinc_ch<2>(a, device, st, tb);
 	return launch_sinc_ch<1>(a, device, st, tb);

@@ -388,8 +388,8 @@ static int dispatch(const StftArgs &a, int log2m, int device, cudaStream_t st) {
 	case 10: return tma_eligible(a) ? launch_tma<10, MAG>(a, device, st) : launch_one<10, MAG>(a, device, st);
 	case 11: return tma_eligible(a) ? launch_tma<11, MAG>(a, device, st) : launch_one<11, MAG>(a, device, st);
 	case 12: return tma_eligible(a) ? launch_tma<12, MAG>(a, device, st) : launch_one<12, MAG>(a, device, st);
-	case 13: return launch_one<13, MAG>(a, device, st);
-	case 14: return launch_one<14, MAG>(a, device, st);
+	case 13:
+	case 14: return launch_stft_mid(a, log2m, device, st);     // whole frame in shared memory, two-level
 	}
 	set_error("stft: n_fft*zeropad must be a power of two in [32, 32768]");
 	return PAR_EUNSUPPORTED;

@@ -64,13 +64,21 @@ for n_fft in (1024, 4096, 16384, 65536):
         s /= np.sqrt(n_fft)
         return s
     tc_med, _ = timed(cufft, 5)
-    for name, fn, nbytes in (("stft complex", lambda: ours(False), C * (n * 4 + T * F * 8)),
-                             ("stft magnitude", lambda: ours(True), C * (n * 4 + T * F * 4))):
+    y = torch.empty((C, n), dtype=torch.float32, device=dev)
+
+    def inverse():
+        _lib.check(L.par_istft_f32(S.data_ptr(), n_fft, T, F, C, T * F, hop, win.ctypes.data, n_fft // 2, n, y.data_ptr(), 1,
+                                   n, _lib.PAR_DEVICE_PTRS, 0, stream), "istft")
+    stages = [("stft complex", lambda: ours(False), C * (n * 4 + T * F * 8)),
+              ("stft magnitude", lambda: ours(True), C * (n * 4 + T * F * 4))]
+    if n_fft <= 32768:
+        stages.append(("istft", inverse, C * (n * 4 + T * F * 8)))
+    for name, fn, nbytes in stages:
         med, best = timed(fn)
         gbs = nbytes / med / 1e6
         print(f"| {n_fft} | {hop} | {name} | {med:.3f} | {best:.3f} | {nbytes / 1e9:.3f} | {gbs:.0f} | {gbs / peak:.3f} | "
-              f"{tc_med:.3f} |")
-    del S, M
+              f"{tc_med if name.startswith('stft') else float('nan'):.3f} |")
+    del S, M, y
 curve = bench.wow_curve(dur, sr)
 st, sp = np.ascontiguousarray(curve[:, 0] * sr), np.ascontiguousarray(curve[:, 1])
 cap = int(n * 1.02) + 4096
