@@ -74,6 +74,10 @@ PAR_API double par_last_kernel_ms(void);
  * n = 2 .. max_n.  Returns the number of mismatches (0 expected), -1 on error. */
 PAR_API int64_t par_selftest_positions_quotient(int64_t max_n, int device);
 
+/* Scratch buffers come from the device's stream-ordered memory pool and stay cached there between
+ * calls (a 10-minute stereo job keeps ~3 GB); this hands the cached blocks back to the driver. */
+PAR_API int par_release_cached_memory(int device);
+
 /* Pinned host allocations (the Python layer returns ndarrays backed by these so that the
  * device->host copy of a result runs at full PCIe rate). */
 PAR_API void *par_host_alloc(int64_t bytes);

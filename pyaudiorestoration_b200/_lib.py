@@ -23,7 +23,7 @@ PAR_TRACE_PEAK, PAR_TRACE_PEAK_TRACK, PAR_TRACE_COG = 0, 1, 2
 
 EXPORTS = (
     "par_last_error", "par_version", "par_device_count", "par_kernel_launch_count",
-    "par_last_kernel_ms", "par_selftest_positions_quotient", "par_host_alloc", "par_host_free", "par_stft_num_frames", "par_stft_f32",
+    "par_last_kernel_ms", "par_selftest_positions_quotient", "par_release_cached_memory", "par_host_alloc", "par_host_free", "par_stft_num_frames", "par_stft_f32",
     "par_istft_f32", "par_speed_segments", "par_speed_to_pos_f64", "par_sinc_resample_f32",
     "par_linear_resample_f32", "par_varispeed_f32", "par_stft_range_f32", "par_resample_range_f32", "par_speed_to_pos_range_f64", "par_trace_f32", "par_stft_trace_f32",
 )
@@ -50,6 +50,8 @@ def _declare(L):
     L.par_last_kernel_ms.restype = dbl
     L.par_selftest_positions_quotient.restype = i64
     L.par_selftest_positions_quotient.argtypes = [i64, i32]
+    L.par_release_cached_memory.restype = i32
+    L.par_release_cached_memory.argtypes = [i32]
     L.par_host_alloc.restype = vp
     L.par_host_alloc.argtypes = [i64]
     L.par_host_free.restype = None
@@ -164,6 +166,16 @@ class _Pinned:
         # keep this object (and with it the allocation) alive as long as any view exists
         buf._pinned_owner = self
         return arr
+
+
+def release_cached_memory():
+    """Return the library's cached device scratch and pinned host buffers to the driver."""
+    with _Pinned._free_lock:
+        cached, _Pinned._free = _Pinned._free, {}
+    for ptrs in cached.values():
+        for p in ptrs:
+            lib().par_host_free(p)
+    check(lib().par_release_cached_memory(device()), "par_release_cached_memory")
 
 
 def pinned_empty(shape, dtype):

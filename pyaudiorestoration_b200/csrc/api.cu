@@ -435,6 +435,16 @@ PAR_API void *par_host_alloc(int64_t bytes) {
 }
 PAR_API void par_host_free(void *p) { if (p) cudaFreeHost(p); }
 
+PAR_API int par_release_cached_memory(int device) {
+	int rc = use_device(device);
+	if (rc != PAR_OK) return rc;
+	PAR_CUDA(cudaDeviceSynchronize());
+	cudaMemPool_t pool;
+	PAR_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+	PAR_CUDA(cudaMemPoolTrimTo(pool, 0));
+	return PAR_OK;
+}
+
 PAR_API int64_t par_stft_num_frames(int64_t n, int n_fft, int hop) {
 	if (n < 1 || n_fft < 2 || hop < 1) return 0;
 	return (n + 2 * (int64_t)(n_fft / 2) - n_fft) / hop + 1;

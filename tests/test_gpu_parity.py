@@ -750,3 +750,15 @@ def test_concurrent_calls_from_threads(fourier, resampling):
     for k in range(4):
         for a, b in zip(results[k], serial[k]):
             assert np.array_equal(a, b)
+
+
+def test_release_cached_memory(par, fourier):
+    import torch
+    from pyaudiorestoration_b200 import _lib
+    x = synth(2_000_000, 17)
+    a = np.array(fourier.stft(x, 4096, 1024))
+    free0, _ = torch.cuda.mem_get_info(_lib.device())
+    _lib.release_cached_memory()
+    free1, _ = torch.cuda.mem_get_info(_lib.device())
+    assert free1 >= free0
+    assert np.array_equal(np.array(fourier.stft(x, 4096, 1024)), a)      # and everything still works afterwards
