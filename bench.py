@@ -71,7 +71,7 @@ def wow_curve(duration, sr, hop=HOP, depth=0.01, freq=0.5556):
 
 # ------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """Samples SM clock / throttle reasons of one GPU every 100 ms on a thread (NVML)."""
+    """Samples SM clock / throttle reasons of one GPU every 20 ms on a thread (NVML)."""
 
     def __init__(self, index):
         self.index, self.samples, self.reasons = index, [], set()
@@ -101,7 +101,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.02)
 
     def start(self):
         if self.nv:
