@@ -16,9 +16,16 @@
 //     fixed point (fc needs more than float32 precision: its error is multiplied by up to NT).
 // Positions, the rounding to the nearest input sample, the fractional shift and fc are
 // float64 like the reference; the tap loop is float32 (parity bound 1e-6, see tests).
+#include <limits.h>
 #include <stdlib.h>
 
+#include <map>
+#include <memory>
+#include <mutex>
+#include <vector>
+
 #include "par_internal.h"
+#include "sinc_core.cuh"
 #include "../../include/par_b200.h"
 
 namespace par {
@@ -206,243 +213,47 @@ int launch_expand_positions(const double *speeds_dev, const int64_t *seg_n_dev,
 }
 
 // ------------------------------------------------------------------------------------------
-// windowed-sinc interpolation
+// windowed-sinc interpolation (arithmetic: sinc_core.cuh)
 // ------------------------------------------------------------------------------------------
+//
+// One tile = SINC_TILE consecutive outputs of one channel group, handled by a CTA of 256 threads:
+//   A  every output's float64 set-up (position -> nearest sample, fractional shift, fc, fixed-point
+//      phases) by one thread per output; the tile's input span by a 32-bit redux over the tile;
+//   B  the set-ups go to shared memory; the span is staged PLANAR in shared memory (coalesced loads,
+//      every input sample leaves HBM once per tile); a block scan forms the work UNITS: an output
+//      whose tap run starts at an even input index (E) followed by one starting at the next index (O)
+//      become one unit, anything else is a unit of its own;
+//   C  one thread per unit runs all 2*NT taps of its one or two outputs from the same 8-byte sample
+//      pairs (sinc_unit), all channels of the group sharing the weights;
+//   D  outputs at the edges of the signal (fewer than 2*NT taps, the reference's start-edge
+//      misalignment) and tiles whose span does not fit take the scalar path that reads global memory.
+// Which path an output takes and the arithmetic applied to it depend only on the positions, never on
+// the tile or the chunk of a host call it falls into.
 
-constexpr int SINC_TILE = 256;       // outputs per block iteration == threads per block
+constexpr int SINC_THREADS = 256;
+constexpr int SINC_TILE = 496;       // outputs per tile: ~248 units + room for 16 unpaired outputs in one round
+constexpr int SINC_XPAD = 16;        // zeroed floats behind the staged span (pairs with zero coefficients read them)
 #ifndef SINC_MIN_BLOCKS
-#define SINC_MIN_BLOCKS 3
+#define SINC_MIN_BLOCKS 2
 #endif
-constexpr int SINC_XPAD = 32;        // zero padding behind the staged span (the last tap block may overhang)
 
-__device__ __forceinline__ float rcp_approx(float x) {
-	float r;
-	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-	return r;
-}
+constexpr unsigned SO_LIVE = 1u, SO_FAST = 2u, SO_LOWPASS = 4u;
 
-// sin/cos of the angle  pi * phase / 2^63  (phase wraps at one full turn = 2^64).
-// The top 32 bits are split into the nearest quarter turn and a residual in [-pi/4, pi/4) that is
-// converted to float32 (absolute error <= 5e-8 rad) and fed to Taylor polynomials whose truncation
-// error is < 2e-9 on that interval.
-__device__ __forceinline__ void sincos_fx(uint64_t phase, float *s, float *c) {
-	const uint32_t t = (uint32_t)(phase >> 32);
-	const uint32_t quad = (t + 0x20000000u) >> 30;
-	const int32_t res = (int32_t)(t - (quad << 30));
-	const float x = (float)res * 1.4629180792671596e-9f;      // pi / 2^31
-	const float x2 = x * x;
-	float ps = fmaf(x2, 2.7557319e-6f, -1.9841270e-4f);
-	ps = fmaf(x2, ps, 8.3333333e-3f);
-	ps = fmaf(x2, ps, -1.6666667e-1f);
-	const float sn = fmaf(x * x2, ps, x);
-	float pc = fmaf(x2, -2.7557319e-7f, 2.4801587e-5f);
-	pc = fmaf(x2, pc, -1.3888889e-3f);
-	pc = fmaf(x2, pc, 4.1666667e-2f);
-	pc = fmaf(x2, pc, -0.5f);
-	const float cs = fmaf(x2, pc, 1.0f);
-	const float a = (quad & 1) ? cs : sn;
-	const float b = (quad & 1) ? sn : cs;
-	*s = (quad & 2) ? -a : a;
-	*c = ((quad + 1) & 2) ? -b : b;
-}
-
-struct SampleSetup {
-	int64_t lower;     // first input sample of the tap run
-	int cnt;           // number of taps (0 .. 2NT)
-	int koff;          // weight index of tap 0 (0 unless PAR_SINC_ALIGNED_EDGES at the start edge)
-	float s;           // fractional shift p - round(p), never exactly 0
-	float fc;          // fc rounded to float32 (centre tap only)
-	bool lowpass;      // fc < 1
-	uint64_t f_fx;     // fc in units of 2^-63 half-turns
-	int64_t s_fx;      // fc * s in the same units
-};
-
-// float64 part of util/resampling.py:67-84 for output i
-__device__ __forceinline__ SampleSetup sample_setup(const SincArgs &a, int64_t i) {
-	SampleSetup su;
-	const int nt = a.nt;
-	const double *pos = a.pos - a.pos_origin;
-	const double p = pos[i];
-	double per;
-	if (i + 1 < a.m) per = fmax(1e-12, pos[i + 1] - p);
-	else per = a.m >= 2 ? fmax(1e-12, pos[a.m - 1] - pos[a.m - 2]) : 0.0;
-	double fc = 1.0 / per;
-	if (!(fc < 1.0)) fc = 1.0;
-	double pr = rint(p);                        // half to even, like Python's round()
-	if (!(pr > -9.0e15)) pr = -9.0e15;          // NaN / -inf guard (garbage in, zeros out)
-	if (pr > 9.0e15) pr = 9.0e15;
-	const long long ind = (long long)pr;
-	const double sd = p - pr;
-	long long lower = ind - nt, upper = ind + nt;
-	if (lower < 0) lower = 0;
-	if (upper > a.n_in) upper = a.n_in;
-	su.lower = lower;
-	su.cnt = upper > lower ? (int)(upper - lower) : 0;
-	su.koff = a.aligned_edges ? (int)(lower - (ind - nt)) : 0;
-	float s = (float)sd;
-	if (s == 0.f) s = 1e-30f;
-	su.s = s;
-	su.lowpass = fc < 1.0;
-	su.fc = (float)fc;
-	su.f_fx = 0;
-	su.s_fx = 0;
-	if (su.lowpass) {
-		su.f_fx = __double2ull_rn(fc * 9223372036854775808.0);
-		su.s_fx = __double2ll_rn(fc * sd * 9223372036854775808.0);
-	}
-	return su;
-}
-
-// Per-sample rotation table of the fc < 1 path: (cos, sin)(j * pi * fc), j = 1 .. 15.
-// j = 1,2,3,4,8,12 are evaluated exactly from the fixed-point angle, the rest are one complex
-// product of two exact entries (absolute error ~1e-7).
-struct RotTable {
-	float c[16], s[16];
-	__device__ __forceinline__ void build(uint64_t f_fx) {
-		c[0] = 1.f; s[0] = 0.f;
-#pragma unroll
-		for (int j = 1; j <= 4; j++) sincos_fx(f_fx * (uint64_t)j, &s[j], &c[j]);
-		sincos_fx(f_fx * 8ull, &s[8], &c[8]);
-		sincos_fx(f_fx * 12ull, &s[12], &c[12]);
-#pragma unroll
-		for (int hi = 4; hi <= 12; hi += 4) {
-#pragma unroll
-			for (int lo = 1; lo <= 3; lo++) {
-				c[hi + lo] = fmaf(c[hi], c[lo], -s[hi] * s[lo]);
-				s[hi + lo] = fmaf(s[hi], c[lo], c[hi] * s[lo]);
-			}
-		}
-	}
-};
-
-// One block of 16 taps (weight indices 16b .. 16b+15) of one output sample, all CH channels.
-// xrow points at the shared-memory sample that pairs with weight index 0 (channel-interleaved).
-//   fc == 1: w = c[widx] / (d - s)                      (sinpi(s) is applied once at the end)
-//   fc <  1: w = hp[widx] * sin(theta_b + j*pi*fc) / (d - s), theta_b exact per block
-template <int CH, bool LOWPASS, bool DESC>
-__device__ __forceinline__ void tap_block(const SampleSetup &su, int b, int nt, const float *tab_s,
-                                          const RotTable &rot, float sa, float ca, float centre_sn, const float *xrow,
-                                          float (&acc)[CH]) {
-	const int d0 = 16 * b - nt;
-	const bool near = d0 < 16 && d0 > -31;       // block holds a tap with |d| < 16
-	const float base = (float)d0 - su.s;         // far blocks: |q| >= 15.5, one rounding is harmless
-	const float4 *t4 = reinterpret_cast<const float4 *>(tab_s + 16 * b);
-#pragma unroll
-	for (int h = 0; h < 2; h++) {
-		const int hh = DESC ? 1 - h : h;
-		const float4 ta = t4[2 * hh], tb = t4[2 * hh + 1];
-		const float coef[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
-		float w[8];
-		if (!LOWPASS && !near) {
-			// far taps of the fc == 1 path: one reciprocal serves two neighbouring taps,
-			//   1/q = (q+1) * t,  1/(q+1) = q * t,  t = 1/(q (q+1)),
-			// which halves the load on the MUFU pipe (the limiter of this path); |q| >= 15.5 here,
-			// so the extra roundings cost ~2e-7 relative on weights below 0.02
-#pragma unroll
-			for (int u = 0; u < 8; u += 2) {
-				const float q = base + (float)(8 * hh + u);
-				const float t = rcp_approx(fmaf(q, q, q));
-				w[u] = fmaf(coef[u], q, coef[u]) * t;
-				w[u + 1] = (coef[u + 1] * q) * t;
-			}
-		} else
-#pragma unroll
-		for (int u = 0; u < 8; u++) {
-			const int j = 8 * hh + u;
-			const float q = near ? (float)(d0 + j) - su.s : base + (float)j;
-			float num = coef[u];
-			if (LOWPASS) {
-				float sn = fmaf(sa, rot.c[j], ca * rot.s[j]);
-				// centre tap (|q| <= 0.5): the fixed-point angle has ABSOLUTE accuracy only, but
-				// sin(pi fc q) / q needs RELATIVE accuracy as q -> 0
-				if (near && d0 == -j) sn = centre_sn;
-				num *= sn;
-			}
-			w[u] = num * rcp_approx(q);
-		}
-#pragma unroll
-		for (int u = 0; u < 8; u++) {
-			const int uu = DESC ? 7 - u : u;
-			const float *xp = xrow + (16 * b + 8 * hh + uu) * CH;
-			if (CH == 1) {
-				acc[0] = fmaf(xp[0], w[uu], acc[0]);
-			} else if (CH == 2) {
-				const float2 v = *reinterpret_cast<const float2 *>(xp);
-				acc[0] = fmaf(v.x, w[uu], acc[0]);
-				acc[1] = fmaf(v.y, w[uu], acc[1]);
-			} else {
-#pragma unroll
-				for (int c4 = 0; c4 < CH; c4 += 4) {
-					const float4 v = *reinterpret_cast<const float4 *>(xp + c4);
-					acc[c4] = fmaf(v.x, w[uu], acc[c4]);
-					acc[c4 + 1] = fmaf(v.y, w[uu], acc[c4 + 1]);
-					acc[c4 + 2] = fmaf(v.z, w[uu], acc[c4 + 2]);
-					acc[c4 + 3] = fmaf(v.w, w[uu], acc[c4 + 3]);
-				}
-			}
-		}
-	}
-}
-
-// All 2*NT taps of an interior output sample whose inputs are staged in shared memory.
-// Summation order: the weights decay like 1/|d| away from the centre tap, so each half of the tap
-// run is accumulated from its far end towards the centre (small terms first) in its own
-// accumulator; a plain left-to-right float32 sum costs ~1e-6 relative at NT >= 128.
-template <int CH, bool LOWPASS>
-__device__ __forceinline__ void taps_fast(const SampleSetup &su, int nt, int nblk, const float *tab_s,
-                                          const float *xrow, float (&out)[CH]) {
-	RotTable rot;
-	float centre_sn = 0.f, s16 = 0.f, c16 = 1.f;
-	if (LOWPASS) {
-		rot.build(su.f_fx);
-		sincos_fx(su.f_fx * 16ull, &s16, &c16);
-		centre_sn = sinpif(su.fc * (0.f - su.s));     // numerator of the d = 0 tap, q = -s
-	}
-	float accl[CH], accr[CH];
-#pragma unroll
-	for (int c = 0; c < CH; c++) accl[c] = accr[c] = 0.f;
-	const int half = nblk >> 1;
-	// Block anchors sin/cos(pi fc (d0 - s)): exact from the fixed-point phase at the far end of each
-	// side and at every 4th block counted from the centre (always the block next to the centre);
-	// in between, one rotation by 16*pi*fc per block (error <= ~1e-7 per step, at |d| >= 16 only).
-	float sal = 0.f, cal = 1.f, sar = 0.f, car = 1.f;
-	for (int it = 0; it < half; it++) {
-		const int bl = it, br = nblk - 1 - it;
-		if (LOWPASS) {
-			if (it == 0 || ((half - 1 - it) & 3) == 0) {
-				sincos_fx(su.f_fx * (uint64_t)(int64_t)(16 * bl - nt) - (uint64_t)su.s_fx, &sal, &cal);
-				sincos_fx(su.f_fx * (uint64_t)(int64_t)(16 * br - nt) - (uint64_t)su.s_fx, &sar, &car);
-			} else {
-				const float nsl = fmaf(sal, c16, cal * s16), ncl = fmaf(cal, c16, -sal * s16);
-				const float nsr = fmaf(sar, c16, -car * s16), ncr = fmaf(car, c16, sar * s16);
-				sal = nsl; cal = ncl; sar = nsr; car = ncr;
-			}
-		}
-		tap_block<CH, LOWPASS, false>(su, bl, nt, tab_s, rot, sal, cal, centre_sn, xrow, accl);
-		tap_block<CH, LOWPASS, true>(su, br, nt, tab_s, rot, sar, car, centre_sn, xrow, accr);
-	}
-	if (nblk & 1) {
-		if (LOWPASS) sincos_fx(su.f_fx * (uint64_t)(int64_t)(16 * half - nt) - (uint64_t)su.s_fx, &sal, &cal);
-		tap_block<CH, LOWPASS, false>(su, half, nt, tab_s, rot, sal, cal, centre_sn, xrow, accl);
-	}
-#pragma unroll
-	for (int c = 0; c < CH; c++) out[c] = accl[c] + accr[c];
-}
-
-// Weight of weight-index widx, any sample (edge / fallback path).
-__device__ __forceinline__ float weight_single(const SampleSetup &su, int widx, int nt,
+// Weight of weight-index widx, any sample (edge / fallback path): h[k] fc sinc(fc (d - s)).
+__device__ __forceinline__ float weight_single(const SincSetup &su, int widx, int nt,
                                                const float *__restrict__ ctab, const float *__restrict__ hptab) {
 	const int d = widx - nt;
-	const float q = (float)d - su.s;
-	if (!su.lowpass) return __ldg(ctab + widx) * rcp_approx(q);
+	const float q = (float)d - su.slot.s;
+	if (!su.lowpass) return __ldg(ctab + widx) * sc_rcp(q);
 	float sn, cs;
-	if (d == 0) sn = sinpif(su.fc * q);
-	else sincos_fx(su.f_fx * (uint64_t)(int64_t)d - (uint64_t)su.s_fx, &sn, &cs);
-	return __ldg(hptab + widx) * sn * rcp_approx(q);
+	if (d == 0) sn = sinpif(su.slot.fc * q);
+	else sincos_fx(su.f_fx * (uint64_t)(int64_t)d - (uint64_t)su.slot.s_fx, &sn, &cs);
+	return __ldg(hptab + widx) * sn * sc_rcp(q);
 }
 
-// Edge / fallback path: any tap count, samples read from global memory, same summation order.
-__device__ __forceinline__ float taps_slow(const SampleSetup &su, int nt, const float *__restrict__ ctab,
+// Edge / fallback path: any tap count, samples read from global memory; each half of the tap run is
+// accumulated from its far end towards the centre.
+__device__ __forceinline__ float taps_slow(const SincSetup &su, int nt, const float *__restrict__ ctab,
                                            const float *__restrict__ hptab, const float *__restrict__ x,
                                            int64_t stride) {
 	float accl = 0.f, accr = 0.f;
@@ -451,131 +262,256 @@ __device__ __forceinline__ float taps_slow(const SampleSetup &su, int nt, const 
 		accl = fmaf(__ldg(x + (su.lower + k) * stride), weight_single(su, k + su.koff, nt, ctab, hptab), accl);
 	for (int k = su.cnt - 1; k >= mid; k--)
 		accr = fmaf(__ldg(x + (su.lower + k) * stride), weight_single(su, k + su.koff, nt, ctab, hptab), accr);
-	return accl + accr;
+	float y = accl + accr;
+	if (!su.lowpass) y *= sinpif(su.slot.s);
+	return y;
 }
 
-template <int CH>
-__global__ void __launch_bounds__(SINC_TILE, CH >= 8 ? 2 : SINC_MIN_BLOCKS)
-sinc_kernel(SincArgs a, const float *__restrict__ ctab, const float *__restrict__ hptab, int nblk, int span_cap) {
-	extern __shared__ __align__(16) float smem_f[];
-	// [c table | hp table] (16 * (nblk + 1) floats each), then the staged samples:
-	// (span_cap + SINC_XPAD) samples x CH, channel-interleaved
-	float *ctab_s = smem_f;
-	float *hptab_s = smem_f + 16 * (nblk + 1);
-	float *xs = smem_f + 32 * (nblk + 1);
-	__shared__ long long red_lo[SINC_TILE / 32], red_hi[SINC_TILE / 32];
+__device__ __forceinline__ SincSetup sinc_setup_at(const SincArgs &a, int64_t i) {
+	const double *pos = a.pos - a.pos_origin;
+	const double p = pos[i];
+	double per;
+	if (i + 1 < a.m) per = fmax(1e-12, pos[i + 1] - p);
+	else per = a.m >= 2 ? fmax(1e-12, pos[a.m - 1] - pos[a.m - 2]) : 0.0;
+	return sinc_setup(p, per, a.nt, a.n_in, a.aligned_edges != 0);
+}
+
+struct SincSmem {
+	int lo[SINC_TILE + 2];         // first tap index relative to the tile's staged span
+	float s[SINC_TILE];
+	float fc[SINC_TILE];
+	unsigned flags[SINC_TILE + 2];
+	unsigned long long g[SINC_TILE];
+	long long sfx[SINC_TILE];
+	int unit[SINC_TILE];           // first output of the unit | paired << 16
+	int red[2][SINC_THREADS / 32];
+	int wsum[SINC_THREADS / 32];
+};
+
+template <int CH, int CAP>
+__global__ void __launch_bounds__(SINC_THREADS, SINC_MIN_BLOCKS)
+sinc_kernel(const __grid_constant__ SincArgs a, const __grid_constant__ SincTab<CAP> tab, const float centre_c,
+            const float *__restrict__ ctab, const float *__restrict__ hptab, const int span_cap) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	SincSmem &sm = *reinterpret_cast<SincSmem *>(smem_raw);
+	float *xs = reinterpret_cast<float *>(smem_raw + ((sizeof(SincSmem) + 15) & ~(size_t)15));
+	const int xpitch = span_cap + SINC_XPAD;            // even
 	const int nt = a.nt;
-	for (int i = threadIdx.x; i < 16 * (nblk + 1); i += SINC_TILE) {
-		ctab_s[i] = __ldg(ctab + i);
-		hptab_s[i] = __ldg(hptab + i);
-	}
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int64_t tiles = (a.out_end - a.out_begin + SINC_TILE - 1) / SINC_TILE;
 	const int groups = (a.n_ch + CH - 1) / CH;
 	const int64_t work = tiles * groups;
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
 	for (int64_t wk = blockIdx.x; wk < work; wk += gridDim.x) {
 		const int grp = (int)(wk / tiles);
 		const int64_t tile = wk - (int64_t)grp * tiles;
 		const int ch0 = grp * CH;
-		const int64_t i = a.out_begin + tile * SINC_TILE + threadIdx.x;
-		const bool live = i < a.out_end;
+		const int64_t i0 = a.out_begin + tile * SINC_TILE;
 
-		SampleSetup su;
-		su.lower = 0; su.cnt = 0; su.koff = 0; su.s = 1e-30f; su.fc = 1.f; su.lowpass = false; su.f_fx = 0; su.s_fx = 0;
-		long long lo = LLONG_MAX, hi = LLONG_MIN;
-		if (live) {
-			su = sample_setup(a, i);
-			if (su.cnt > 0) { lo = su.lower; hi = su.lower + su.cnt; }
-		}
-		// ---- input span of the tile ----
+		// ---- A: set-up of outputs tid and tid + 256, tile span ----
+		const double p_first = (a.pos - a.pos_origin)[i0];
+		double rf = rint(p_first);
+		if (!(rf > -9.0e15)) rf = -9.0e15;
+		if (rf > 9.0e15) rf = 9.0e15;
+		const long long ref = (long long)rf - nt;
+		SincSetup su[2];
+		bool live[2], fast[2];
+		int lo_min = INT_MAX, hi_max = INT_MIN;
 #pragma unroll
-		for (int o = 16; o > 0; o >>= 1) {
-			lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-			hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+		for (int r = 0; r < 2; r++) {
+			const int o = tid + r * SINC_THREADS;
+			const int64_t i = i0 + o;
+			live[r] = o < SINC_TILE && i < a.out_end;
+			fast[r] = false;
+			if (live[r]) {
+				su[r] = sinc_setup_at(a, i);
+				fast[r] = su[r].cnt == 2 * nt && su[r].koff == 0;
+				if (fast[r]) {
+					long long rel = su[r].lower - ref;
+					rel = rel < -(1ll << 30) ? -(1ll << 30) : (rel > (1ll << 30) ? (1ll << 30) : rel);
+					lo_min = min(lo_min, (int)rel);
+					hi_max = max(hi_max, (int)rel + 2 * nt);
+				}
+			}
 		}
-		if (lane == 0) { red_lo[warp] = lo; red_hi[warp] = hi; }
+		lo_min = __reduce_min_sync(0xffffffffu, lo_min);
+		hi_max = __reduce_max_sync(0xffffffffu, hi_max);
+		if (lane == 0) { sm.red[0][warp] = lo_min; sm.red[1][warp] = hi_max; }
 		__syncthreads();
-		long long tlo = red_lo[0], thi = red_hi[0];
 #pragma unroll
-		for (int w = 1; w < SINC_TILE / 32; w++) { tlo = min(tlo, red_lo[w]); thi = max(thi, red_hi[w]); }
-		const bool any = thi > tlo;
-		const bool staged = any && (thi - tlo) <= span_cap;
+		for (int w = 0; w < SINC_THREADS / 32; w++) { lo_min = min(lo_min, sm.red[0][w]); hi_max = max(hi_max, sm.red[1][w]); }
+		const long long tlo = (ref + lo_min) & ~1ll;      // even absolute index (lower >= 0 on the fast path)
+		const bool any = hi_max > lo_min;
+		const int span = any ? (int)(ref + hi_max - tlo) : 0;
+		const bool staged = any && lo_min > -(1 << 30) && hi_max < (1 << 30) && span <= span_cap;
+
+		// ---- B: set-ups to shared memory, stage the span, form the units ----
+#pragma unroll
+		for (int r = 0; r < 2; r++) {
+			const int o = tid + r * SINC_THREADS;
+			if (o < SINC_TILE) {
+				const bool f = fast[r] && staged;
+				sm.flags[o] = (live[r] ? SO_LIVE : 0u) | (f ? SO_FAST : 0u) | (live[r] && su[r].lowpass ? SO_LOWPASS : 0u);
+				if (f) {
+					sm.lo[o] = (int)(su[r].lower - tlo);
+					sm.s[o] = su[r].slot.s;
+					sm.fc[o] = su[r].slot.fc;
+					sm.g[o] = su[r].slot.g_fx;
+					sm.sfx[o] = su[r].slot.s_fx;
+				} else {
+					sm.lo[o] = -1;
+				}
+			}
+		}
+		if (tid < 2) { sm.flags[SINC_TILE + tid] = 0u; sm.lo[SINC_TILE + tid] = -1; }
 		if (staged) {
-			const int total = ((int)(thi - tlo) + SINC_XPAD) * CH;
-			const int valid = (int)(thi - tlo);
-			for (int idx = threadIdx.x; idx < total; idx += SINC_TILE) {
-				const int e = idx / CH, c = idx - e * CH;
-				float v = 0.f;
-				if (e < valid && ch0 + c < a.n_ch)
-					v = __ldg(a.signal + (int64_t)(ch0 + c) * a.sig_ch_stride + (tlo + e - a.sig_origin) * a.sig_stride);
-				xs[idx] = v;
+			const int len = span + SINC_XPAD;
+#pragma unroll
+			for (int c = 0; c < CH; c++) {
+				const bool have = ch0 + c < a.n_ch;
+				const float *src = a.signal + (int64_t)(ch0 + c) * a.sig_ch_stride + (tlo - a.sig_origin) * a.sig_stride;
+				for (int e = tid; e < len; e += SINC_THREADS)
+					xs[c * xpitch + e] = (have && e < span) ? __ldg(src + (int64_t)e * a.sig_stride) : 0.f;
 			}
 		}
 		__syncthreads();
-
-		float acc[CH];
-#pragma unroll
-		for (int c = 0; c < CH; c++) acc[c] = 0.f;
-		// per-sample choice (not per warp): the result of a sample must not depend on which other
-		// samples share its warp, i.e. on how a host-pointer call was cut into chunks
-		const bool interior = su.cnt == 2 * nt && su.koff == 0;
-		if (live && su.cnt > 0) {
-			if (staged && interior) {
-				const float *xrow = xs + (int)(su.lower - tlo) * CH;
-#if defined(SINC_EXPERIMENT_SKIP_TAPS)          // development aid (scripts/try_variants.sh): fixed cost only
-				acc[0] = xrow[0] * su.s + (float)su.f_fx;
-#elif defined(SINC_EXPERIMENT_ALL_FC1)
-				taps_fast<CH, false>(su, nt, nblk, ctab_s, xrow, acc);
-#elif defined(SINC_EXPERIMENT_ALL_LOWPASS)
-				taps_fast<CH, true>(su, nt, nblk, hptab_s, xrow, acc);
-#else
-				if (su.lowpass) taps_fast<CH, true>(su, nt, nblk, hptab_s, xrow, acc);
-				else taps_fast<CH, false>(su, nt, nblk, ctab_s, xrow, acc);
-#endif
-			} else {
-				// first / last NT outputs of a file, or a span too wide for shared memory
-#pragma unroll
-				for (int c = 0; c < CH; c++)
-					if (ch0 + c < a.n_ch)
-						acc[c] = taps_slow(su, nt, ctab, hptab,
-						                   a.signal + (int64_t)(ch0 + c) * a.sig_ch_stride - a.sig_origin * a.sig_stride,
-						                   a.sig_stride);
+		int n_units = 0;
+		{
+			// outputs 2 tid and 2 tid + 1: a unit starts at every fast output that is not the O half of a pair
+			const int o = 2 * tid;
+			bool st0 = false, st1 = false, hd0 = false, hd1 = false;
+			if (o < SINC_TILE) {
+				const unsigned fm = sm.flags[o > 0 ? o - 1 : SINC_TILE], f0 = sm.flags[o], f1 = sm.flags[o + 1], f2 = sm.flags[o + 2];
+				const int lm = sm.lo[o > 0 ? o - 1 : SINC_TILE], l0 = sm.lo[o], l1 = sm.lo[o + 1], l2 = sm.lo[o + 2];
+				const bool hdm = o > 0 && (fm & f0 & SO_FAST) && !(lm & 1) && l0 == lm + 1 && !((fm ^ f0) & SO_LOWPASS);
+				hd0 = (f0 & f1 & SO_FAST) && !(l0 & 1) && l1 == l0 + 1 && !((f0 ^ f1) & SO_LOWPASS);
+				hd1 = (f1 & f2 & SO_FAST) && !(l1 & 1) && l2 == l1 + 1 && !((f1 ^ f2) & SO_LOWPASS);
+				st0 = (f0 & SO_FAST) && !hdm;
+				st1 = (f1 & SO_FAST) && !hd0;
 			}
-			if (!su.lowpass) {
-				const float sp = sinpif(su.s);
+			const int cnt = (int)st0 + (int)st1;
+			int inc = cnt;
 #pragma unroll
-				for (int c = 0; c < CH; c++) acc[c] *= sp;
+			for (int d = 1; d < 32; d <<= 1) {
+				const int v = __shfl_up_sync(0xffffffffu, inc, d);
+				if (lane >= d) inc += v;
+			}
+			if (lane == 31) sm.wsum[warp] = inc;
+			__syncthreads();
+			int base = 0;
+#pragma unroll
+			for (int w = 0; w < SINC_THREADS / 32; w++) {
+				if (w < warp) base += sm.wsum[w];
+				n_units += sm.wsum[w];
+			}
+			int idx = base + inc - cnt;
+			if (st0) sm.unit[idx++] = o | (hd0 ? 0x10000 : 0);
+			if (st1) sm.unit[idx] = (o + 1) | (hd1 ? 0x10000 : 0);
+		}
+		__syncthreads();
+
+		// ---- C: one thread per unit ----
+		for (int u = tid; u < n_units; u += SINC_THREADS) {
+			const int code = sm.unit[u];
+			const int o = code & 0xffff;
+			const bool paired = (code >> 16) != 0;
+			const int lo0 = sm.lo[o];
+			const int oE = (paired || !(lo0 & 1)) ? o : -1;
+			const int oO = paired ? o + 1 : ((lo0 & 1) ? o : -1);
+			const int j0 = lo0 & ~1;
+			const bool lowpass = (sm.flags[o] & SO_LOWPASS) != 0;
+			SincSlot E, O;
+			E.s = 0.5f; E.fc = 1.f; E.g_fx = 0; E.s_fx = 0;
+			O = E;
+			if (oE >= 0) { E.s = sm.s[oE]; E.fc = sm.fc[oE]; E.g_fx = sm.g[oE]; E.s_fx = sm.sfx[oE]; }
+			if (oO >= 0) { O.s = sm.s[oO]; O.fc = sm.fc[oO]; O.g_fx = sm.g[oO]; O.s_fx = sm.sfx[oO]; }
+			float yE[CH], yO[CH];
+#if defined(SINC_EXPERIMENT_SKIP_TAPS)            // development aid: everything but the tap loop
+#pragma unroll
+			for (int c = 0; c < CH; c++) { yE[c] = xs[c * xpitch + j0] * E.s; yO[c] = xs[c * xpitch + j0 + 1] * O.s + (float)O.g_fx; }
+#elif defined(SINC_EXPERIMENT_ALL_FC1)
+			sinc_unit<CH, false>(nt, tab.full, centre_c, xs + j0, xpitch, E, O, yE, yO);
+#elif defined(SINC_EXPERIMENT_ALL_LOWPASS)
+			sinc_unit<CH, true>(nt, tab.lp, centre_c, xs + j0, xpitch, E, O, yE, yO);
+#else
+			if (lowpass) sinc_unit<CH, true>(nt, tab.lp, centre_c, xs + j0, xpitch, E, O, yE, yO);
+			else sinc_unit<CH, false>(nt, tab.full, centre_c, xs + j0, xpitch, E, O, yE, yO);
+#endif
+#pragma unroll
+			for (int c = 0; c < CH; c++) {
+				if (ch0 + c < a.n_ch) {
+					float *dst = a.out + (int64_t)(ch0 + c) * a.out_ch_stride - a.out_origin * a.out_stride;
+					if (oE >= 0) dst[(i0 + oE) * a.out_stride] = yE[c];
+					if (oO >= 0) dst[(i0 + oO) * a.out_stride] = yO[c];
+				}
 			}
 		}
-		if (live) {
+
+		// ---- D: edge outputs / unstaged tiles ----
 #pragma unroll
-			for (int c = 0; c < CH; c++)
-				if (ch0 + c < a.n_ch) a.out[(int64_t)(ch0 + c) * a.out_ch_stride + (i - a.out_origin) * a.out_stride] = acc[c];
+		for (int r = 0; r < 2; r++) {
+			if (live[r] && !(fast[r] && staged)) {
+				const int64_t i = i0 + tid + r * SINC_THREADS;
+				for (int c = 0; c < CH; c++) {
+					if (ch0 + c >= a.n_ch) break;
+					float y = 0.f;
+					if (su[r].cnt > 0)
+						y = taps_slow(su[r], nt, ctab, hptab,
+						              a.signal + (int64_t)(ch0 + c) * a.sig_ch_stride - a.sig_origin * a.sig_stride, a.sig_stride);
+					a.out[(int64_t)(ch0 + c) * a.out_ch_stride + (i - a.out_origin) * a.out_stride] = y;
+				}
+			}
 		}
 		__syncthreads();
 	}
 }
 
-template <int CH>
+// C[k] of sinc_core.cuh per NT, packed for the E / O slots (host cache, passed to the kernel by value)
+template <int CAP>
+static const SincTab<CAP> *sinc_param_table(int nt, float *centre_c) {
+	static std::mutex mu;
+	static std::map<int, std::unique_ptr<SincTab<CAP>>> cache;
+	std::lock_guard<std::mutex> lk(mu);
+	auto it = cache.find(nt);
+	if (it == cache.end()) {
+		std::unique_ptr<SincTab<CAP>> t(new SincTab<CAP>());
+		sinc_fill_table<CAP>(nt, t.get());
+		it = cache.emplace(nt, std::move(t)).first;
+	}
+	const SincTab<CAP> *t = it->second.get();
+	// centre coefficient C[NT]: entry m = nt/2, lane by parity
+	*centre_c = (nt & 1) ? t->full[nt / 2].y : t->full[nt / 2].x;
+	return t;
+}
+
+template <int CH, int CAP>
 static int launch_sinc_ch(const SincArgs &a, int device, cudaStream_t st, const SincTables &tb) {
-	// widest span staged in shared memory: a tile read at up to 4x speed
-	const int span_cap = 4 * SINC_TILE + 2 * a.nt;
-	const int smem = (CH * (span_cap + SINC_XPAD) + 2 * tb.padded) * (int)sizeof(float);
-	auto kern = sinc_kernel<CH>;
+	// widest span staged in shared memory: a tile read at up to ~2.5x speed
+	int span_cap = (5 * SINC_TILE) / 2 + 2 * a.nt + 2;
+	span_cap = (span_cap + 3) & ~3;
+	const int smem = (int)((sizeof(SincSmem) + 15) & ~(size_t)15) + CH * (span_cap + SINC_XPAD) * (int)sizeof(float);
+	auto kern = sinc_kernel<CH, CAP>;
 	PAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 	int occ = 0;
-	PAR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SINC_TILE, smem));
+	PAR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SINC_THREADS, smem));
 	if (occ < 1) occ = 1;
 	const int64_t tiles = (a.out_end - a.out_begin + SINC_TILE - 1) / SINC_TILE;
 	const int64_t work = tiles * ((a.n_ch + CH - 1) / CH);
 	int64_t grid = (int64_t)occ * sm_count(device);
 	if (grid > work) grid = work;
 	if (grid < 1) return PAR_OK;
-	kern<<<(unsigned)grid, SINC_TILE, smem, st>>>(a, tb.c, tb.hp, tb.padded / 16 - 1, span_cap);
+	float centre_c = 0.f;
+	const SincTab<CAP> *pt = sinc_param_table<CAP>(a.nt, &centre_c);
+	kern<<<(unsigned)grid, SINC_THREADS, smem, st>>>(a, *pt, centre_c, tb.c, tb.hp, span_cap);
 	count_launch();
 	PAR_CUDA(cudaGetLastError());
 	return PAR_OK;
+}
+
+template <int CH>
+static int launch_sinc_cap(const SincArgs &a, int device, cudaStream_t st, const SincTables &tb) {
+	if (sinc_num_blocks(a.nt) * SINC_PAIRS_PER_BLOCK <= SINC_TAB_SMALL) return launch_sinc_ch<CH, SINC_TAB_SMALL>(a, device, st, tb);
+	return launch_sinc_ch<CH, SINC_TAB_LARGE>(a, device, st, tb);
 }
 
 int launch_sinc(const SincArgs &a, int device, cudaStream_t st) {
@@ -583,15 +519,10 @@ int launch_sinc(const SincArgs &a, int device, cudaStream_t st) {
 	SincTables tb;
 	int rc = sinc_tables(device, a.nt, st, &tb);
 	if (rc != PAR_OK) return rc;
-	// The tap weights of an output sample are computed once per channel group.  Groups of 4 are the
-	// sweet spot: a group of 8 needs 128 registers (2 CTAs/SM) and is shared-memory-bandwidth bound
-	// just like two groups of 4 -- measured 25 % slower on the 8-channel config ($PAR_B200_SINC_CH8=1
-	// selects it for experiments).
-	static const bool ch8 = getenv("PAR_B200_SINC_CH8") && atoi(getenv("PAR_B200_SINC_CH8")) > 0;
-	if (ch8 && a.n_ch >= 8) return launch_sinc_ch<8>(a, device, st, tb);
-	if (a.n_ch >= 4) return launch_sinc_ch<4>(a, device, st, tb);
-	if (a.n_ch >= 2) return launch_sinc_ch<2>(a, device, st, tb);
-	return launch_sinc_ch<1>(a, device, st, tb);
+	// The tap weights of an output are computed once per channel group of up to 4 channels.
+	if (a.n_ch >= 4) return launch_sinc_cap<4>(a, device, st, tb);
+	if (a.n_ch >= 2) return launch_sinc_cap<2>(a, device, st, tb);
+	return launch_sinc_cap<1>(a, device, st, tb);
 }
 
 // ------------------------------------------------------------------------------------------
