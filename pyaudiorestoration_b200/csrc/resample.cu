@@ -230,9 +230,13 @@ int launch_expand_positions(const double *speeds_dev, const int64_t *seg_n_dev,
 // Which path an output takes and the arithmetic applied to it depend only on the positions, never on
 // the tile or the chunk of a host call it falls into.
 
-constexpr int SINC_THREADS = 256;
-constexpr int SINC_TILE = 496;       // outputs per tile: ~248 units + room for 16 unpaired outputs in one round
-constexpr int SINC_XPAD = 16;        // zeroed floats behind the staged span (pairs with zero coefficients read them)
+#ifndef SINC_THREADS_N
+#define SINC_THREADS_N 256
+#endif
+constexpr int SINC_THREADS = SINC_THREADS_N;
+constexpr int SINC_TILE = 2 * SINC_THREADS - 16;   // outputs per tile: ~T/2 units + room for 16 unpaired outputs in one round
+constexpr int SINC_XPAD = 16;        // zeroed floats behind the staged span (block padding with zero coefficients reads them)
+constexpr int SINC_XFRONT = 8;       // ... and in front of it
 #ifndef SINC_MIN_BLOCKS
 #define SINC_MIN_BLOCKS 2
 #endif
@@ -276,41 +280,88 @@ __device__ __forceinline__ SincSetup sinc_setup_at(const SincArgs &a, int64_t i)
 	return sinc_setup(p, per, a.nt, a.n_in, a.aligned_edges != 0);
 }
 
-struct SincSmem {
-	int lo[SINC_TILE + 2];         // first tap index relative to the tile's staged span
-	float s[SINC_TILE];
-	float fc[SINC_TILE];
+// cp.async (LDGSTS): global -> shared copies that land while the CTA interpolates the previous tile
+__device__ __forceinline__ void cp_async4(void *dst, const void *src) {
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Per-tile shared-memory state (double-buffered: tile w+1 is prepared while tile w is interpolated).
+struct SincTileBuf {
+	double pos[SINC_TILE + 2];     // read positions of the tile's outputs (+ the one after), prefetched
+	unsigned long long g[SINC_TILE + 2];   // entry SINC_TILE of g, sfx, s, fc: a harmless stand-in for the empty half of a unit
+	long long sfx[SINC_TILE + 2];
+	int lo[SINC_TILE + 2];         // centre tap index relative to the tile's staged span (-1: not on the fast path)
+	float s[SINC_TILE + 2];
+	float fc[SINC_TILE + 2];
 	unsigned flags[SINC_TILE + 2];
-	unsigned long long g[SINC_TILE];
-	long long sfx[SINC_TILE];
 	int unit[SINC_TILE];           // first output of the unit | paired << 16
+};
+struct SincSmem {
+	SincTileBuf tb[2];
 	int red[2][SINC_THREADS / 32];
 	int wsum[SINC_THREADS / 32];
 };
 
+// Uniform (per-CTA) description of a prepared tile, kept in registers by every thread.
+struct SincTileInfo {
+	int64_t i0;        // first output
+	long long tlo;     // absolute input index of the staged span's first sample (multiple of 4)
+	int span;          // staged samples
+	int n_units;
+	int ch0;
+	bool staged;
+};
+
 template <int CH, int CAP>
 __global__ void __launch_bounds__(SINC_THREADS, SINC_MIN_BLOCKS)
-sinc_kernel(const __grid_constant__ SincArgs a, const __grid_constant__ SincTab<CAP> tab, const float centre_c,
+sinc_kernel(const __grid_constant__ SincArgs a, const __grid_constant__ SincTab<CAP> tab,
             const float *__restrict__ ctab, const float *__restrict__ hptab, const int span_cap) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	SincSmem &sm = *reinterpret_cast<SincSmem *>(smem_raw);
-	float *xs = reinterpret_cast<float *>(smem_raw + ((sizeof(SincSmem) + 15) & ~(size_t)15));
-	const int xpitch = span_cap + SINC_XPAD;            // even
+	float *xs_all = reinterpret_cast<float *>(smem_raw + ((sizeof(SincSmem) + 15) & ~(size_t)15));
+	const int xpitch = SINC_XFRONT + span_cap + SINC_XPAD;            // multiple of 4
 	const int nt = a.nt;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int64_t tiles = (a.out_end - a.out_begin + SINC_TILE - 1) / SINC_TILE;
 	const int groups = (a.n_ch + CH - 1) / CH;
 	const int64_t work = tiles * groups;
+	// contiguous work ranges: consecutive tiles of a CTA are neighbours in memory
+	const int64_t per_cta = (work + gridDim.x - 1) / gridDim.x;
+	const int64_t w0 = (int64_t)blockIdx.x * per_cta;
+	const int64_t w1 = w0 + per_cta < work ? w0 + per_cta : work;
+	if (w0 >= w1) return;
+	const double *posg = a.pos - a.pos_origin;
+	for (int e = tid; e < 2 * CH * SINC_XFRONT; e += SINC_THREADS) {          // front padding of both buffers (both parity planes)
+		const int bufi = e / (CH * SINC_XFRONT), r = e % (CH * SINC_XFRONT), par = r / (CH * SINC_XFRONT / 2), q = r % (CH * SINC_XFRONT / 2);
+		xs_all[bufi * CH * xpitch + par * (xpitch / 2) * CH + q] = 0.f;
+	}
 
-	for (int64_t wk = blockIdx.x; wk < work; wk += gridDim.x) {
-		const int grp = (int)(wk / tiles);
-		const int64_t tile = wk - (int64_t)grp * tiles;
-		const int ch0 = grp * CH;
+	// positions of work item w -> tb[buf].pos (asynchronous)
+	auto prefetch_pos = [&](int64_t w, int buf) {
+		const int64_t tile = w % tiles;
 		const int64_t i0 = a.out_begin + tile * SINC_TILE;
+		int64_t cnt = a.m - i0;
+		if (cnt > SINC_TILE + 1) cnt = SINC_TILE + 1;
+		for (int e = tid; e < cnt; e += SINC_THREADS) cp_async8(&sm.tb[buf].pos[e], posg + i0 + e);
+	};
 
-		// ---- A: set-up of outputs tid and tid + 256, tile span ----
-		const double p_first = (a.pos - a.pos_origin)[i0];
-		double rf = rint(p_first);
+	// set-up of work item w from tb[buf].pos: per-output records, span, units; returns the tile description
+	auto prepare = [&](int64_t w, int buf) -> SincTileInfo {
+		SincTileBuf &tb = sm.tb[buf];
+		SincTileInfo ti;
+		const int grp = (int)(w / tiles);
+		const int64_t tile = w - (int64_t)grp * tiles;
+		ti.ch0 = grp * CH;
+		ti.i0 = a.out_begin + tile * SINC_TILE;
+		double rf = rint(tb.pos[0]);
 		if (!(rf > -9.0e15)) rf = -9.0e15;
 		if (rf > 9.0e15) rf = 9.0e15;
 		const long long ref = (long long)rf - nt;
@@ -320,11 +371,15 @@ sinc_kernel(const __grid_constant__ SincArgs a, const __grid_constant__ SincTab<
 #pragma unroll
 		for (int r = 0; r < 2; r++) {
 			const int o = tid + r * SINC_THREADS;
-			const int64_t i = i0 + o;
+			const int64_t i = ti.i0 + o;
 			live[r] = o < SINC_TILE && i < a.out_end;
 			fast[r] = false;
 			if (live[r]) {
-				su[r] = sinc_setup_at(a, i);
+				const double p = tb.pos[o];
+				double per;
+				if (i + 1 < a.m) per = fmax(1e-12, tb.pos[o + 1] - p);
+				else per = a.m >= 2 ? fmax(1e-12, posg[a.m - 1] - posg[a.m - 2]) : 0.0;
+				su[r] = sinc_setup(p, per, nt, a.n_in, a.aligned_edges != 0);
 				fast[r] = su[r].cnt == 2 * nt && su[r].koff == 0;
 				if (fast[r]) {
 					long long rel = su[r].lower - ref;
@@ -339,136 +394,169 @@ sinc_kernel(const __grid_constant__ SincArgs a, const __grid_constant__ SincTab<
 		if (lane == 0) { sm.red[0][warp] = lo_min; sm.red[1][warp] = hi_max; }
 		__syncthreads();
 #pragma unroll
-		for (int w = 0; w < SINC_THREADS / 32; w++) { lo_min = min(lo_min, sm.red[0][w]); hi_max = max(hi_max, sm.red[1][w]); }
-		const long long tlo = (ref + lo_min) & ~1ll;      // even absolute index (lower >= 0 on the fast path)
+		for (int wv = 0; wv < SINC_THREADS / 32; wv++) { lo_min = min(lo_min, sm.red[0][wv]); hi_max = max(hi_max, sm.red[1][wv]); }
+		ti.tlo = (ref + lo_min) & ~3ll;               // multiple of 4 (lower >= 0 on the fast path)
 		const bool any = hi_max > lo_min;
-		const int span = any ? (int)(ref + hi_max - tlo) : 0;
-		const bool staged = any && lo_min > -(1 << 30) && hi_max < (1 << 30) && span <= span_cap;
-
-		// ---- B: set-ups to shared memory, stage the span, form the units ----
+		ti.span = any ? (int)(ref + hi_max - ti.tlo) : 0;
+		ti.staged = any && lo_min > -(1 << 30) && hi_max < (1 << 30) && ti.span <= span_cap;
 #pragma unroll
 		for (int r = 0; r < 2; r++) {
 			const int o = tid + r * SINC_THREADS;
 			if (o < SINC_TILE) {
-				const bool f = fast[r] && staged;
-				sm.flags[o] = (live[r] ? SO_LIVE : 0u) | (f ? SO_FAST : 0u) | (live[r] && su[r].lowpass ? SO_LOWPASS : 0u);
+				const bool f = fast[r] && ti.staged;
+				tb.flags[o] = (live[r] ? SO_LIVE : 0u) | (f ? SO_FAST : 0u) | (live[r] && su[r].lowpass ? SO_LOWPASS : 0u);
 				if (f) {
-					sm.lo[o] = (int)(su[r].lower - tlo);
-					sm.s[o] = su[r].slot.s;
-					sm.fc[o] = su[r].slot.fc;
-					sm.g[o] = su[r].slot.g_fx;
-					sm.sfx[o] = su[r].slot.s_fx;
+					tb.lo[o] = (int)(su[r].lower - ti.tlo) + nt;
+					tb.s[o] = su[r].slot.s;
+					tb.fc[o] = su[r].slot.fc;
+					tb.g[o] = su[r].slot.g_fx;
+					tb.sfx[o] = su[r].slot.s_fx;
 				} else {
-					sm.lo[o] = -1;
+					tb.lo[o] = -1;
 				}
 			}
 		}
-		if (tid < 2) { sm.flags[SINC_TILE + tid] = 0u; sm.lo[SINC_TILE + tid] = -1; }
-		if (staged) {
-			const int len = span + SINC_XPAD;
-#pragma unroll
-			for (int c = 0; c < CH; c++) {
-				const bool have = ch0 + c < a.n_ch;
-				const float *src = a.signal + (int64_t)(ch0 + c) * a.sig_ch_stride + (tlo - a.sig_origin) * a.sig_stride;
-				for (int e = tid; e < len; e += SINC_THREADS)
-					xs[c * xpitch + e] = (have && e < span) ? __ldg(src + (int64_t)e * a.sig_stride) : 0.f;
-			}
+		if (tid < 2) {
+			tb.flags[SINC_TILE + tid] = 0u; tb.lo[SINC_TILE + tid] = -1;
+			tb.s[SINC_TILE + tid] = 0.5f; tb.fc[SINC_TILE + tid] = 1.f; tb.g[SINC_TILE + tid] = 0; tb.sfx[SINC_TILE + tid] = 0;
 		}
 		__syncthreads();
-		int n_units = 0;
-		{
-			// outputs 2 tid and 2 tid + 1: a unit starts at every fast output that is not the O half of a pair
-			const int o = 2 * tid;
-			bool st0 = false, st1 = false, hd0 = false, hd1 = false;
-			if (o < SINC_TILE) {
-				const unsigned fm = sm.flags[o > 0 ? o - 1 : SINC_TILE], f0 = sm.flags[o], f1 = sm.flags[o + 1], f2 = sm.flags[o + 2];
-				const int lm = sm.lo[o > 0 ? o - 1 : SINC_TILE], l0 = sm.lo[o], l1 = sm.lo[o + 1], l2 = sm.lo[o + 2];
-				const bool hdm = o > 0 && (fm & f0 & SO_FAST) && !(lm & 1) && l0 == lm + 1 && !((fm ^ f0) & SO_LOWPASS);
-				hd0 = (f0 & f1 & SO_FAST) && !(l0 & 1) && l1 == l0 + 1 && !((f0 ^ f1) & SO_LOWPASS);
-				hd1 = (f1 & f2 & SO_FAST) && !(l1 & 1) && l2 == l1 + 1 && !((f1 ^ f2) & SO_LOWPASS);
-				st0 = (f0 & SO_FAST) && !hdm;
-				st1 = (f1 & SO_FAST) && !hd0;
-			}
-			const int cnt = (int)st0 + (int)st1;
-			int inc = cnt;
-#pragma unroll
-			for (int d = 1; d < 32; d <<= 1) {
-				const int v = __shfl_up_sync(0xffffffffu, inc, d);
-				if (lane >= d) inc += v;
-			}
-			if (lane == 31) sm.wsum[warp] = inc;
-			__syncthreads();
-			int base = 0;
-#pragma unroll
-			for (int w = 0; w < SINC_THREADS / 32; w++) {
-				if (w < warp) base += sm.wsum[w];
-				n_units += sm.wsum[w];
-			}
-			int idx = base + inc - cnt;
-			if (st0) sm.unit[idx++] = o | (hd0 ? 0x10000 : 0);
-			if (st1) sm.unit[idx] = (o + 1) | (hd1 ? 0x10000 : 0);
+		// units: outputs 2 tid and 2 tid + 1; a unit starts at every fast output that is not the O half of a pair
+		const int o = 2 * tid;
+		bool st0 = false, st1 = false, hd0 = false, hd1 = false;
+		if (o < SINC_TILE) {
+			const unsigned fm = tb.flags[o > 0 ? o - 1 : SINC_TILE], f0 = tb.flags[o], f1 = tb.flags[o + 1], f2 = tb.flags[o + 2];
+			const int lm = tb.lo[o > 0 ? o - 1 : SINC_TILE], l0 = tb.lo[o], l1 = tb.lo[o + 1], l2 = tb.lo[o + 2];
+			const bool hdm = o > 0 && (fm & f0 & SO_FAST) && !(lm & 1) && l0 == lm + 1 && !((fm ^ f0) & SO_LOWPASS);
+			hd0 = (f0 & f1 & SO_FAST) && !(l0 & 1) && l1 == l0 + 1 && !((f0 ^ f1) & SO_LOWPASS);
+			hd1 = (f1 & f2 & SO_FAST) && !(l1 & 1) && l2 == l1 + 1 && !((f1 ^ f2) & SO_LOWPASS);
+			st0 = (f0 & SO_FAST) && !hdm;
+			st1 = (f1 & SO_FAST) && !hd0;
 		}
+		const int cnt = (int)st0 + (int)st1;
+		int inc = cnt;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const int v = __shfl_up_sync(0xffffffffu, inc, d);
+			if (lane >= d) inc += v;
+		}
+		if (lane == 31) sm.wsum[warp] = inc;
 		__syncthreads();
+		int base = 0;
+		ti.n_units = 0;
+#pragma unroll
+		for (int wv = 0; wv < SINC_THREADS / 32; wv++) {
+			if (wv < warp) base += sm.wsum[wv];
+			ti.n_units += sm.wsum[wv];
+		}
+		int idx = base + inc - cnt;
+		if (st0) tb.unit[idx++] = o | (hd0 ? 0x10000 : 0);
+		if (st1) tb.unit[idx] = (o + 1) | (hd1 ? 0x10000 : 0);
+		return ti;
+	};
 
-		// ---- C: one thread per unit ----
-		for (int u = tid; u < n_units; u += SINC_THREADS) {
-			const int code = sm.unit[u];
+	// the tile's input span -> xs buffer `buf` (asynchronous, channel-interleaved), zero padding behind it
+	auto stage_span = [&](const SincTileInfo &ti, int buf) {
+		if (!ti.staged) return;
+		float *xs = xs_all + buf * CH * xpitch;
+		const int plane = (xpitch / 2) * CH;
+		const int len = ti.span + SINC_XPAD;
+#pragma unroll
+		for (int c = 0; c < CH; c++) {
+			const bool have = ti.ch0 + c < a.n_ch;
+			const float *src = a.signal + (int64_t)(ti.ch0 + c) * a.sig_ch_stride + (ti.tlo - a.sig_origin) * a.sig_stride;
+			for (int e = tid; e < len; e += SINC_THREADS) {
+				const int P = e + SINC_XFRONT;
+				float *dst = xs + (P & 1) * plane + (P >> 1) * CH + c;
+				if (have && e < ti.span) cp_async4(dst, src + (int64_t)e * a.sig_stride);
+				else *dst = 0.f;
+			}
+		}
+	};
+
+	prefetch_pos(w0, 0);
+	cp_async_commit();
+	cp_async_wait_all();
+	__syncthreads();
+	SincTileInfo cur = prepare(w0, 0);
+	stage_span(cur, 0);
+	if (w0 + 1 < w1) prefetch_pos(w0 + 1, 1);
+	cp_async_commit();
+
+	for (int64_t w = w0; w < w1; w++) {
+		const int buf = (int)((w - w0) & 1);
+		cp_async_wait_all();            // this tile's samples and the next tile's positions have landed
+		__syncthreads();
+		SincTileInfo nxt = cur;
+		if (w + 1 < w1) {
+			nxt = prepare(w + 1, buf ^ 1);
+			stage_span(nxt, buf ^ 1);
+			if (w + 2 < w1) prefetch_pos(w + 2, buf);     // tb[buf].pos is no longer needed
+			cp_async_commit();
+		}
+		__syncthreads();                // unit table of the next tile / of the first tile complete
+		const SincTileBuf &tb = sm.tb[buf];
+		const float *xs = xs_all + buf * CH * xpitch;
+
+		// ---- one thread per unit ----
+		for (int u = tid; u < cur.n_units; u += SINC_THREADS) {
+			const int code = tb.unit[u];
 			const int o = code & 0xffff;
 			const bool paired = (code >> 16) != 0;
-			const int lo0 = sm.lo[o];
+			const int lo0 = tb.lo[o];
 			const int oE = (paired || !(lo0 & 1)) ? o : -1;
 			const int oO = paired ? o + 1 : ((lo0 & 1) ? o : -1);
 			const int j0 = lo0 & ~1;
-			const bool lowpass = (sm.flags[o] & SO_LOWPASS) != 0;
-			SincSlot E, O;
-			E.s = 0.5f; E.fc = 1.f; E.g_fx = 0; E.s_fx = 0;
-			O = E;
-			if (oE >= 0) { E.s = sm.s[oE]; E.fc = sm.fc[oE]; E.g_fx = sm.g[oE]; E.s_fx = sm.sfx[oE]; }
-			if (oO >= 0) { O.s = sm.s[oO]; O.fc = sm.fc[oO]; O.g_fx = sm.g[oO]; O.s_fx = sm.sfx[oO]; }
-			float yE[CH], yO[CH];
+			const bool lowpass = (tb.flags[o] & SO_LOWPASS) != 0;
+			const int iE = oE >= 0 ? oE : SINC_TILE, iO = oO >= 0 ? oO : SINC_TILE;
+			const SincSlotRef sl[2] = {{&tb.s[iE], &tb.fc[iE], &tb.g[iE], &tb.sfx[iE]}, {&tb.s[iO], &tb.fc[iO], &tb.g[iO], &tb.sfx[iO]}};
+			float y[2][CH];
+			const SincWin<CH> xu{xs + ((SINC_XFRONT + j0) >> 1) * CH, (xpitch / 2) * CH};
 #if defined(SINC_EXPERIMENT_SKIP_TAPS)            // development aid: everything but the tap loop
 #pragma unroll
-			for (int c = 0; c < CH; c++) { yE[c] = xs[c * xpitch + j0] * E.s; yO[c] = xs[c * xpitch + j0 + 1] * O.s + (float)O.g_fx; }
+			for (int c = 0; c < CH; c++) { y[0][c] = xu.at(0)[c] * *sl[0].s; y[1][c] = xu.at(1)[c] * *sl[1].s + (float)*sl[1].g_fx; }
 #elif defined(SINC_EXPERIMENT_ALL_FC1)
-			sinc_unit<CH, false>(nt, tab.full, centre_c, xs + j0, xpitch, E, O, yE, yO);
+			sinc_unit<CH, false, 2, CAP>(nt, tab, xu, sl, y);
 #elif defined(SINC_EXPERIMENT_ALL_LOWPASS)
-			sinc_unit<CH, true>(nt, tab.lp, centre_c, xs + j0, xpitch, E, O, yE, yO);
+			sinc_unit<CH, true, 2, CAP>(nt, tab, xu, sl, y);
 #else
-			if (lowpass) sinc_unit<CH, true>(nt, tab.lp, centre_c, xs + j0, xpitch, E, O, yE, yO);
-			else sinc_unit<CH, false>(nt, tab.full, centre_c, xs + j0, xpitch, E, O, yE, yO);
+			if (lowpass) sinc_unit<CH, true, 2, CAP>(nt, tab, xu, sl, y);
+			else sinc_unit<CH, false, 2, CAP>(nt, tab, xu, sl, y);
 #endif
 #pragma unroll
 			for (int c = 0; c < CH; c++) {
-				if (ch0 + c < a.n_ch) {
-					float *dst = a.out + (int64_t)(ch0 + c) * a.out_ch_stride - a.out_origin * a.out_stride;
-					if (oE >= 0) dst[(i0 + oE) * a.out_stride] = yE[c];
-					if (oO >= 0) dst[(i0 + oO) * a.out_stride] = yO[c];
+				if (cur.ch0 + c < a.n_ch) {
+					float *dst = a.out + (int64_t)(cur.ch0 + c) * a.out_ch_stride - a.out_origin * a.out_stride;
+					if (oE >= 0) dst[(cur.i0 + oE) * a.out_stride] = y[0][c];
+					if (oO >= 0) dst[(cur.i0 + oO) * a.out_stride] = y[1][c];
 				}
 			}
 		}
 
-		// ---- D: edge outputs / unstaged tiles ----
+		// ---- edge outputs / unstaged tiles: scalar path from global memory ----
 #pragma unroll
 		for (int r = 0; r < 2; r++) {
-			if (live[r] && !(fast[r] && staged)) {
-				const int64_t i = i0 + tid + r * SINC_THREADS;
+			const int o = tid + r * SINC_THREADS;
+			if (o < SINC_TILE && (tb.flags[o] & SO_LIVE) && !(tb.flags[o] & SO_FAST)) {
+				const int64_t i = cur.i0 + o;
+				const SincSetup su = sinc_setup_at(a, i);
 				for (int c = 0; c < CH; c++) {
-					if (ch0 + c >= a.n_ch) break;
+					if (cur.ch0 + c >= a.n_ch) break;
 					float y = 0.f;
-					if (su[r].cnt > 0)
-						y = taps_slow(su[r], nt, ctab, hptab,
-						              a.signal + (int64_t)(ch0 + c) * a.sig_ch_stride - a.sig_origin * a.sig_stride, a.sig_stride);
-					a.out[(int64_t)(ch0 + c) * a.out_ch_stride + (i - a.out_origin) * a.out_stride] = y;
+					if (su.cnt > 0)
+						y = taps_slow(su, nt, ctab, hptab,
+						              a.signal + (int64_t)(cur.ch0 + c) * a.sig_ch_stride - a.sig_origin * a.sig_stride, a.sig_stride);
+					a.out[(int64_t)(cur.ch0 + c) * a.out_ch_stride + (i - a.out_origin) * a.out_stride] = y;
 				}
 			}
 		}
-		__syncthreads();
+		cur = nxt;
 	}
 }
 
-// C[k] of sinc_core.cuh per NT, packed for the E / O slots (host cache, passed to the kernel by value)
+// distance table of sinc_core.cuh per NT (host cache, passed to the kernel by value)
 template <int CAP>
-static const SincTab<CAP> *sinc_param_table(int nt, float *centre_c) {
+static const SincTab<CAP> *sinc_param_table(int nt) {
 	static std::mutex mu;
 	static std::map<int, std::unique_ptr<SincTab<CAP>>> cache;
 	std::lock_guard<std::mutex> lk(mu);
@@ -478,18 +566,15 @@ static const SincTab<CAP> *sinc_param_table(int nt, float *centre_c) {
 		sinc_fill_table<CAP>(nt, t.get());
 		it = cache.emplace(nt, std::move(t)).first;
 	}
-	const SincTab<CAP> *t = it->second.get();
-	// centre coefficient C[NT]: entry m = nt/2, lane by parity
-	*centre_c = (nt & 1) ? t->full[nt / 2].y : t->full[nt / 2].x;
-	return t;
+	return it->second.get();
 }
 
 template <int CH, int CAP>
 static int launch_sinc_ch(const SincArgs &a, int device, cudaStream_t st, const SincTables &tb) {
 	// widest span staged in shared memory: a tile read at up to ~2.5x speed
-	int span_cap = (5 * SINC_TILE) / 2 + 2 * a.nt + 2;
+	int span_cap = 2 * SINC_TILE + 2 * a.nt + 8;
 	span_cap = (span_cap + 3) & ~3;
-	const int smem = (int)((sizeof(SincSmem) + 15) & ~(size_t)15) + CH * (span_cap + SINC_XPAD) * (int)sizeof(float);
+	const int smem = (int)((sizeof(SincSmem) + 15) & ~(size_t)15) + 2 * CH * (SINC_XFRONT + span_cap + SINC_XPAD) * (int)sizeof(float);
 	auto kern = sinc_kernel<CH, CAP>;
 	PAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 	int occ = 0;
@@ -500,9 +585,8 @@ static int launch_sinc_ch(const SincArgs &a, int device, cudaStream_t st, const 
 	int64_t grid = (int64_t)occ * sm_count(device);
 	if (grid > work) grid = work;
 	if (grid < 1) return PAR_OK;
-	float centre_c = 0.f;
-	const SincTab<CAP> *pt = sinc_param_table<CAP>(a.nt, &centre_c);
-	kern<<<(unsigned)grid, SINC_THREADS, smem, st>>>(a, *pt, centre_c, tb.c, tb.hp, span_cap);
+	const SincTab<CAP> *pt = sinc_param_table<CAP>(a.nt);
+	kern<<<(unsigned)grid, SINC_THREADS, smem, st>>>(a, *pt, tb.c, tb.hp, span_cap);
 	count_launch();
 	PAR_CUDA(cudaGetLastError());
 	return PAR_OK;
@@ -510,7 +594,7 @@ static int launch_sinc_ch(const SincArgs &a, int device, cudaStream_t st, const 
 
 template <int CH>
 static int launch_sinc_cap(const SincArgs &a, int device, cudaStream_t st, const SincTables &tb) {
-	if (sinc_num_blocks(a.nt) * SINC_PAIRS_PER_BLOCK <= SINC_TAB_SMALL) return launch_sinc_ch<CH, SINC_TAB_SMALL>(a, device, st, tb);
+	if (sinc_num_blocks(a.nt) * (SINC_BLOCK / 2) <= SINC_TAB_SMALL) return launch_sinc_ch<CH, SINC_TAB_SMALL>(a, device, st, tb);
 	return launch_sinc_ch<CH, SINC_TAB_LARGE>(a, device, st, tb);
 }
 

@@ -69,6 +69,17 @@ SC_HD float2 fadd2(float2 a, float2 b) {
 	return make_float2(a.x + b.x, a.y + b.y);
 #endif
 }
+SC_HD float2 fsub2(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__)
+	float2 d;
+	asm("sub.rn.f32x2 %0, %1, %2;"
+	    : "=l"(*reinterpret_cast<uint64_t *>(&d))
+	    : "l"(*reinterpret_cast<const uint64_t *>(&a)), "l"(*reinterpret_cast<const uint64_t *>(&b)));
+	return d;
+#else
+	return make_float2(a.x - b.x, a.y - b.y);
+#endif
+}
 SC_HD float2 bcast2(float v) { return make_float2(v, v); }
 
 SC_HD float sc_rcp(float x) {
@@ -115,20 +126,32 @@ SC_HD void sincos_fx(uint64_t phase, float *s, float *c) {
 }
 
 // ---- coefficient table (a kernel parameter: read through the constant bank with uniform loads) ----
-// Entry m (tap pair m of a thread, absolute input indices j0 + 2m, j0 + 2m + 1):
-//   .x, .y = C[2m], C[2m+1]      E slot (first tap at j0:     weight indices 2m,   2m+1)
-//   .z, .w = C[2m-1], C[2m]      O slot (first tap at j0 + 1: weight indices 2m-1, 2m)
-// with C[k] = 0 outside 0 .. 2NT-1.  `lp` is the same table with the centre coefficient C[NT] zeroed.
+// The Hann window is symmetric, so the two taps at distance d on either side of the centre tap share
+//   C_d = (-1)^(d+1) hanning(2NT+1)[NT +- d] / pi
+// and for an output with fractional shift s (|s| <= 1/2) their weights (times sin(theta), see above) are
+//   w(+d) = C_d / (d - s),   w(-d) = C_d / (-d - s).
+// NEAR distances (d <= 16):   w(+d) = C_d (s + d) t,  w(-d) = C_d (s - d) t,  t = 1 / (d^2 - s^2)
+//     -- one reciprocal and five FMA-pipe operations per tap pair;
+// FAR distances (d > 16):     1 / (d -+ s) as a power series in s / d (|s/d| < 1/33, four terms: the
+//     truncation is < 1e-6 of a weight that is itself < 0.02):
+//     w(+d) = O + E,  w(-d) = E - O,  O = a0 + a2 s^2,  E = s (a1 + a3 s^2),  a_k = C_d / d^(k+1)
+//     -- five FMA-pipe operations per tap pair and NO reciprocal.
+// Entry p holds the distances d = 2p+1 and d' = 2p+2 so that two consecutive distances run as packed pairs:
+//     near:  a = (d^2, d'^2, C_d, C_d'),      b = (C_d d, C_d' d', -C_d d, -C_d' d')
+//     far:   a = (a0_d, a0_d', a2_d, a2_d'),  b = (a1_d, a1_d', a3_d, a3_d')
+// Distances past NT-1 (block padding) have all-zero far entries.  c0 is the centre coefficient C_0.
 template <int CAP>
 struct SincTab {
-	float4 full[CAP];
-	float4 lp[CAP];
+	float4 a[CAP];
+	float4 b[CAP];
+	float c0;
 };
-constexpr int SINC_TAB_SMALL = 132;     // NT <= 128 (+ padding to whole blocks of 4 pairs)
-constexpr int SINC_TAB_LARGE = 516;     // NT <= 512
-constexpr int SINC_PAIRS_PER_BLOCK = 4;
+constexpr int SINC_TAB_SMALL = 64;      // NT <= 128: (NT - 1) distances in pairs, padded to whole blocks of 8
+constexpr int SINC_TAB_LARGE = 256;     // NT <= 512
+constexpr int SINC_BLOCK = 8;           // distances per block
+constexpr int SINC_NEAR_BLOCKS = 2;     // blocks (from the centre) that use the exact reciprocal form
 
-SC_HD int sinc_num_blocks(int nt) { return (nt + 1 + SINC_PAIRS_PER_BLOCK - 1) / SINC_PAIRS_PER_BLOCK; }
+SC_HD int sinc_num_blocks(int nt) { return (nt - 1 + SINC_BLOCK - 1) / SINC_BLOCK; }
 
 // One interior output sample (all 2NT taps inside the signal, no start-edge shift).
 struct SincSlot {
@@ -138,7 +161,7 @@ struct SincSlot {
 	int64_t s_fx;     // fc * s in the same units
 };
 
-// fc < 1: rotation table (cos, sin)(j pi g), j < 8, as pairs; the step (cos, sin)(8 pi g).
+// fc < 1: rotation table (cos, sin)(j pi g), j < 8, as pairs (j, j+1); the step (cos, sin)(8 pi g).
 // j = 1, 2, 4 and 8 come exactly from the fixed-point angle, 3, 5, 6, 7 are one or two complex products.
 struct SincRot {
 	float2 c[4], s[4];
@@ -162,124 +185,187 @@ struct SincRot {
 	}
 };
 
-// exact block anchor: (sin, cos)(theta_d0), theta_d0 = pi (g d0 + fc s)
-SC_HD void sinc_anchor(const SincSlot &sl, int d0, float *sa, float *ca) {
-	sincos_fx(sl.g_fx * (uint64_t)(int64_t)d0 + (uint64_t)sl.s_fx, sa, ca);
+// Where the set-up of an output lives (shared memory in the kernel): the tap loop re-reads the fixed-point
+// phases when it needs an exact anchor instead of holding them in registers.
+struct SincSlotRef {
+	const float *s, *fc;
+	const unsigned long long *g_fx;
+	const long long *s_fx;
+};
+
+// exact anchor: (sin, cos)(theta_d), theta_d = pi (g d + fc s)
+SC_HD void sinc_anchor(const SincSlotRef &sl, int d, float *sa, float *ca) {
+	sincos_fx((uint64_t)*sl.g_fx * (uint64_t)(int64_t)d + (uint64_t)*sl.s_fx, sa, ca);
 }
 
-// One block of 4 tap pairs (B = block index) for the E and the O output of a thread, all CH channels.
-//   xs    : this thread's pair 0 of channel 0 in the planar staging buffer (8-byte aligned)
-//   xpitch: floats between channels
-//   NEAR  : the block holds a tap with |d| < 16: q = d - s is formed from the exact integer d
-//   DESC  : pairs are visited from high to low (right half of the tap run, accumulated towards the centre)
-template <int CH, bool LOWPASS, bool DESC, bool NEAR>
-SC_HD void sinc_block(int B, int nt, const float4 *tab, const float *xs, int xpitch,
-                      const SincSlot &E, const SincSlot &O, const SincRot &rotE, const SincRot &rotO,
-                      float saE, float caE, float saO, float caO, float2 (&accE)[CH], float2 (&accO)[CH]) {
-	const float d0f = (float)(8 * B - nt);                 // d of the E slot's first tap in this block
-	const float baseE = d0f - E.s, baseO = (d0f - 1.f) - O.s;
-#pragma unroll
-	for (int uu = 0; uu < 4; uu++) {
-		const int u = DESC ? 3 - uu : uu;
-		const int m = 4 * B + u;
-		const float4 c = tab[m];
-		const float2 J = make_float2((float)(2 * u + 1), (float)(2 * u));
-		float2 QE, QO;           // (q of the pair's second tap, q of its first tap) = (q + 1, q)
-		if (NEAR) {
-			const float2 DE = fadd2(J, bcast2(d0f));       // exact small integers
-			QE = fadd2(DE, bcast2(-E.s));
-			QO = fadd2(fadd2(DE, bcast2(-1.f)), bcast2(-O.s));
-		} else {
-			QE = fadd2(J, bcast2(baseE));                  // |q| >= 15: one more rounding is harmless
-			QO = fadd2(J, bcast2(baseO));
-		}
-		const float tE = sc_rcp(QE.x * QE.y), tO = sc_rcp(QO.x * QO.y);
-		float2 nE = fmul2(QE, make_float2(c.x, c.y));      // (C_k0 (q+1), C_k1 q)
-		float2 nO = fmul2(QO, make_float2(c.z, c.w));
-		if (LOWPASS) {
-			const float2 snE = ffma2(bcast2(saE), rotE.c[u], fmul2(bcast2(caE), rotE.s[u]));
-			const float2 snO = ffma2(bcast2(saO), rotO.c[u], fmul2(bcast2(caO), rotO.s[u]));
-			nE = fmul2(nE, snE);
-			nO = fmul2(nO, snO);
-		}
-		const float2 wE = fmul2(nE, bcast2(tE)), wO = fmul2(nO, bcast2(tO));
-#pragma unroll
-		for (int ch = 0; ch < CH; ch++) {
-			const float2 X = *reinterpret_cast<const float2 *>(xs + ch * xpitch + 2 * m);
-			accE[ch] = ffma2(X, wE, accE[ch]);
-			accO[ch] = ffma2(X, wO, accO[ch]);
-		}
+// Channel vectors: the staging buffer is channel-interleaved, x[sample * CH + ch], so one 4/8/16-byte load
+// fetches all channels of a sample and one packed FMA with the broadcast weight updates two channels.
+template <int CH> struct SincVec;
+template <> struct SincVec<1> {
+	float v;
+	SC_HD void zero() { v = 0.f; }
+	SC_HD void load(const float *p) { v = *p; }
+	SC_HD void fma(const SincVec &x, float w) { v = fmaf(x.v, w, v); }
+	SC_HD void add(const SincVec &o) { v += o.v; }
+	SC_HD float get(int) const { return v; }
+};
+template <> struct SincVec<2> {
+	float2 v;
+	SC_HD void zero() { v = make_float2(0.f, 0.f); }
+	SC_HD void load(const float *p) { v = *reinterpret_cast<const float2 *>(p); }
+	SC_HD void fma(const SincVec &x, float w) { v = ffma2(x.v, bcast2(w), v); }
+	SC_HD void add(const SincVec &o) { v = fadd2(v, o.v); }
+	SC_HD float get(int c) const { return c ? v.y : v.x; }
+};
+template <> struct SincVec<4> {
+	float2 a, b;
+	SC_HD void zero() { a = b = make_float2(0.f, 0.f); }
+	SC_HD void load(const float *p) {
+		const float4 t = *reinterpret_cast<const float4 *>(p);
+		a = make_float2(t.x, t.y); b = make_float2(t.z, t.w);
 	}
-}
+	SC_HD void fma(const SincVec &x, float w) { a = ffma2(x.a, bcast2(w), a); b = ffma2(x.b, bcast2(w), b); }
+	SC_HD void add(const SincVec &o) { a = fadd2(a, o.a); b = fadd2(b, o.b); }
+	SC_HD float get(int c) const { return c == 0 ? a.x : c == 1 ? a.y : c == 2 ? b.x : b.y; }
+};
 
-// All taps of the E and O outputs of one thread.  Summation order: the weights decay like 1/|d| away
-// from the centre tap, so each half of the tap run is accumulated from its far end towards the centre
-// (small terms first), even and odd taps in separate lanes: four partial sums per output and channel.
+// Per-output running state of the tap loop.
 template <int CH, bool LOWPASS>
-SC_HD void sinc_unit(int nt, const float4 *tab, float centre_c, const float *xs, int xpitch,
-                     const SincSlot &E, const SincSlot &O, float (&outE)[CH], float (&outO)[CH]) {
-	const int nblk = sinc_num_blocks(nt);
-	const int half = nblk >> 1;
-	SincRot rotE, rotO;
-	if (LOWPASS) {
-		rotE.build(E.g_fx);
-		rotO.build(O.g_fx);
+struct SincAcc {
+	float s, s2;
+	SincVec<CH> accl, accr;
+	float sar, car, sal, ncal;      // fc < 1: (sin, cos) of theta at +d_a and (sin, -cos) at -d_a, d_a = first distance of the block
+};
+
+// Weights of the tap pairs at distances (d, d+1) = (8 b + 2 u + 1, 8 b + 2 u + 2) of one output.
+template <int CH, bool LOWPASS, bool NEAR>
+SC_HD void sinc_pair_weights(const float4 ta, const float4 tb, int u, const SincRot &rot,
+                             const SincAcc<CH, LOWPASS> &A, float2 *wp, float2 *wm) {
+	float2 np, nm;
+	if (NEAR) {
+		const float2 D = fadd2(make_float2(ta.x, ta.y), bcast2(-A.s2));           // d^2 - s^2
+		const float2 t = make_float2(sc_rcp(D.x), sc_rcp(D.y));
+		np = fmul2(ffma2(bcast2(A.s), make_float2(ta.z, ta.w), make_float2(tb.x, tb.y)), t);   // C (s + d) t
+		nm = fmul2(ffma2(bcast2(A.s), make_float2(ta.z, ta.w), make_float2(tb.z, tb.w)), t);   // C (s - d) t
+	} else {
+		const float2 O = ffma2(make_float2(ta.z, ta.w), bcast2(A.s2), make_float2(ta.x, ta.y));
+		const float2 E = fmul2(ffma2(make_float2(tb.z, tb.w), bcast2(A.s2), make_float2(tb.x, tb.y)), bcast2(A.s));
+		np = fadd2(O, E);
+		nm = fsub2(E, O);
 	}
-	float2 aEl[CH], aEr[CH], aOl[CH], aOr[CH];
+	if (LOWPASS) {
+		// sin(theta(+d_a) + j pi g) and sin(theta(-d_a) - j pi g), j = 2u, 2u + 1
+		np = fmul2(np, ffma2(bcast2(A.sar), rot.c[u], fmul2(bcast2(A.car), rot.s[u])));
+		nm = fmul2(nm, ffma2(bcast2(A.sal), rot.c[u], fmul2(bcast2(A.ncal), rot.s[u])));
+	}
+	*wp = np;
+	*wm = nm;
+}
+
+// Staging layout.  A thread interpolates the output E whose centre tap is the EVEN staged sample c and the
+// output O centred at c + 1; consecutive threads have centres 2 samples apart.  To keep every warp-wide load
+// free of bank conflicts the staged samples are split by parity: sample P lives at
+//     x[(P & 1) * plane + (P >> 1) * CH + ch]
+// so that the lanes of a load (same parity, centres 2 apart) read consecutive CH-vectors.
+template <int CH>
+struct SincWin {
+	const float *even;     // the thread's centre sample c (even plane)
+	int plane;             // floats between the parity planes
+	// sample c + off (off known at compile time after unrolling)
+	SC_HD const float *at(int off) const {
+		// floor division by 2 for negative offsets too
+		const int m = (off - (off & 1)) / 2;
+		return even + (off & 1) * plane + m * CH;
+	}
+};
+
+// One block of 8 distances d = 8 b + 1 .. 8 b + 8 (visited from far to near) for the R outputs of a thread
+// (slot r is centred at sample c + r).
+template <int CH, bool LOWPASS, bool NEAR, int R, int CAP>
+SC_HD void sinc_block(int b, const SincTab<CAP> &tab, const SincWin<CH> &x,
+                      const SincRot (&rot)[LOWPASS ? R : 1], SincAcc<CH, LOWPASS> (&A)[R]) {
+	// 8 + R - 1 samples on either side: right[k] = sample c + 8 b + 1 + k, left[k] = sample c - 8 b - 8 + k
+	SincVec<CH> xr[7 + R], xl[7 + R];
+	SincWin<CH> xb = x;
+	xb.even = x.even + 4 * b * CH;
+	SincWin<CH> xa = x;
+	xa.even = x.even - 4 * b * CH;
 #pragma unroll
-	for (int ch = 0; ch < CH; ch++) aEl[ch] = aEr[ch] = aOl[ch] = aOr[ch] = make_float2(0.f, 0.f);
-	float saEl = 0.f, caEl = 1.f, saEr = 0.f, caEr = 1.f, saOl = 0.f, caOl = 1.f, saOr = 0.f, caOr = 1.f;
-	for (int it = 0; it < half; it++) {
-		const int bl = it, br = nblk - 1 - it;
+	for (int k = 0; k < 7 + R; k++) {
+		xr[k].load(xb.at(1 + k));
+		xl[k].load(xa.at(k - 8));
+	}
+#pragma unroll
+	for (int u = 3; u >= 0; u--) {
+		const float4 ta = tab.a[4 * b + u], tb = tab.b[4 * b + u];
+		const int j1 = 2 * u + 1, j2 = 2 * u + 2;              // d - 8 b of the two distances
+#pragma unroll
+		for (int r = 0; r < R; r++) {
+			float2 wp, wm;
+			sinc_pair_weights<CH, LOWPASS, NEAR>(ta, tb, u, rot[LOWPASS ? r : 0], A[r], &wp, &wm);
+			// +d is right[d - 8b - 1 + r], -d is left[8 - (d - 8b) + r]; the farther distance first
+			A[r].accr.fma(xr[j2 - 1 + r], wp.y);
+			A[r].accl.fma(xl[8 - j2 + r], wm.y);
+			A[r].accr.fma(xr[j1 - 1 + r], wp.x);
+			A[r].accl.fma(xl[8 - j1 + r], wm.x);
+		}
+	}
+}
+
+// All taps of the R outputs of one thread.  Summation order: the weights decay like 1/|d| away from the
+// centre tap, so each half of the tap run is accumulated from its far end towards the centre (small terms
+// first) in its own accumulator; the centre tap comes last.
+template <int CH, bool LOWPASS, int R, int CAP>
+SC_HD void sinc_unit(int nt, const SincTab<CAP> &tab, const SincWin<CH> &x,
+                     const SincSlotRef (&sl)[R], float (&out)[R][CH]) {
+	const int nblk = sinc_num_blocks(nt);
+	SincRot rot[LOWPASS ? R : 1];
+	SincAcc<CH, LOWPASS> A[R];
+#pragma unroll
+	for (int r = 0; r < R; r++) {
+		A[r].s = *sl[r].s; A[r].s2 = A[r].s * A[r].s;
+		A[r].accl.zero(); A[r].accr.zero();
+		A[r].sar = A[r].sal = 0.f; A[r].car = 1.f; A[r].ncal = -1.f;
+		if (LOWPASS) rot[r].build(*sl[r].g_fx);
+	}
+	for (int b = nblk - 1; b >= 0; b--) {
 		if (LOWPASS) {
-			if (it == 0 || ((half - 1 - it) & 7) == 0) {
-				sinc_anchor(E, 8 * bl - nt, &saEl, &caEl);
-				sinc_anchor(E, 8 * br - nt, &saEr, &caEr);
-				sinc_anchor(O, 8 * bl - 1 - nt, &saOl, &caOl);
-				sinc_anchor(O, 8 * br - 1 - nt, &saOr, &caOr);
+			const int da = 8 * b + 1;
+			if (b == nblk - 1 || (b & 7) == 0) {
+#pragma unroll
+				for (int r = 0; r < R; r++) {
+					float cl;
+					sinc_anchor(sl[r], da, &A[r].sar, &A[r].car);
+					sinc_anchor(sl[r], -da, &A[r].sal, &cl);
+					A[r].ncal = -cl;
+				}
 			} else {
-				// left anchors advance by +8 pi g, right anchors by -8 pi g
-				const float a = fmaf(saEl, rotE.c8, caEl * rotE.s8), b = fmaf(caEl, rotE.c8, -saEl * rotE.s8);
-				const float c = fmaf(saEr, rotE.c8, -caEr * rotE.s8), d = fmaf(caEr, rotE.c8, saEr * rotE.s8);
-				saEl = a; caEl = b; saEr = c; caEr = d;
-				const float e = fmaf(saOl, rotO.c8, caOl * rotO.s8), f = fmaf(caOl, rotO.c8, -saOl * rotO.s8);
-				const float g = fmaf(saOr, rotO.c8, -caOr * rotO.s8), h = fmaf(caOr, rotO.c8, saOr * rotO.s8);
-				saOl = e; caOl = f; saOr = g; caOr = h;
+				// moving towards the centre: the right anchor turns by -8 pi g, the left one by +8 pi g
+#pragma unroll
+				for (int r = 0; r < R; r++) {
+					const SincRot &q = rot[LOWPASS ? r : 0];
+					const float a = fmaf(A[r].sar, q.c8, -A[r].car * q.s8), b2 = fmaf(A[r].car, q.c8, A[r].sar * q.s8);
+					const float c = fmaf(A[r].sal, q.c8, -A[r].ncal * q.s8), d = fmaf(A[r].ncal, q.c8, A[r].sal * q.s8);
+					A[r].sar = a; A[r].car = b2; A[r].sal = c; A[r].ncal = d;
+				}
 			}
 		}
-		// |d| < 16 somewhere in the block (E and O slots together cover d0 - 1 .. d0 + 7)
-		const bool nearl = 8 * bl + 7 - nt > -16 && 8 * bl - 1 - nt < 16;
-		const bool nearr = 8 * br + 7 - nt > -16 && 8 * br - 1 - nt < 16;
-		if (nearl) sinc_block<CH, LOWPASS, false, true>(bl, nt, tab, xs, xpitch, E, O, rotE, rotO, saEl, caEl, saOl, caOl, aEl, aOl);
-		else sinc_block<CH, LOWPASS, false, false>(bl, nt, tab, xs, xpitch, E, O, rotE, rotO, saEl, caEl, saOl, caOl, aEl, aOl);
-		if (nearr) sinc_block<CH, LOWPASS, true, true>(br, nt, tab, xs, xpitch, E, O, rotE, rotO, saEr, caEr, saOr, caOr, aEr, aOr);
-		else sinc_block<CH, LOWPASS, true, false>(br, nt, tab, xs, xpitch, E, O, rotE, rotO, saEr, caEr, saOr, caOr, aEr, aOr);
+		if (b < SINC_NEAR_BLOCKS) sinc_block<CH, LOWPASS, true, R, CAP>(b, tab, x, rot, A);
+		else sinc_block<CH, LOWPASS, false, R, CAP>(b, tab, x, rot, A);
 	}
-	if (nblk & 1) {
-		if (LOWPASS) {
-			sinc_anchor(E, 8 * half - nt, &saEl, &caEl);
-			sinc_anchor(O, 8 * half - 1 - nt, &saOl, &caOl);
-		}
-		sinc_block<CH, LOWPASS, false, true>(half, nt, tab, xs, xpitch, E, O, rotE, rotO, saEl, caEl, saOl, caOl, aEl, aOl);
-	}
-	if (LOWPASS) {
-		// centre tap: q = -s, sin(theta_0) = sin(pi fc s) with relative accuracy as s -> 0
-		const float wE = centre_c * sc_sinpi(E.fc * E.s) * sc_rcp(-E.s);
-		const float wO = centre_c * sc_sinpi(O.fc * O.s) * sc_rcp(-O.s);
+	// centre tap: q = -s; fc < 1: sin(theta_0) = sin(pi fc s) with relative accuracy as s -> 0
+	const float c0 = tab.c0;
 #pragma unroll
-		for (int ch = 0; ch < CH; ch++) {
-			const float l = aEl[ch].x + aEl[ch].y, r = aEr[ch].x + aEr[ch].y;
-			outE[ch] = fmaf(xs[ch * xpitch + nt], wE, l + r);
-			const float lo = aOl[ch].x + aOl[ch].y, ro = aOr[ch].x + aOr[ch].y;
-			outO[ch] = fmaf(xs[ch * xpitch + nt + 1], wO, lo + ro);
-		}
-	} else {
-		const float spE = sc_sinpi(E.s), spO = sc_sinpi(O.s);
+	for (int r = 0; r < R; r++) {
+		float w = c0 * sc_rcp(-A[r].s);
+		if (LOWPASS) w *= sc_sinpi(*sl[r].fc * A[r].s);
+		const float sp = LOWPASS ? 1.f : sc_sinpi(A[r].s);
+		SincVec<CH> xc;
+		xc.load(x.at(r));
+		A[r].accl.add(A[r].accr);
+		A[r].accl.fma(xc, w);
 #pragma unroll
-		for (int ch = 0; ch < CH; ch++) {
-			outE[ch] = ((aEl[ch].x + aEl[ch].y) + (aEr[ch].x + aEr[ch].y)) * spE;
-			outO[ch] = ((aOl[ch].x + aOl[ch].y) + (aOr[ch].x + aOr[ch].y)) * spO;
-		}
+		for (int ch = 0; ch < CH; ch++) out[r][ch] = LOWPASS ? A[r].accl.get(ch) : A[r].accl.get(ch) * sp;
 	}
 }
 
@@ -331,26 +417,33 @@ SC_HD SincSetup sinc_setup(double p, double per, int nt, int64_t n_in, bool alig
 	return su;
 }
 
-// Host: C[k] per NT, packed for the E / O slots.  Returns the centre coefficient C[NT].
+// Host: the distance table of one NT (float64 arithmetic, rounded once).
 template <int CAP>
-inline float sinc_fill_table(int nt, SincTab<CAP> *t) {
-	float c[2 * 512 + 2];
+inline void sinc_fill_table(int nt, SincTab<CAP> *t) {
 	const int mm = 2 * nt + 1;
-	for (int k = 0; k < 2 * nt; k++) {
-		// np.hanning(2nt+1)[k] rounded to float32 (util/resampling.py:24,36), then the sign of
-		// sin(pi (d - s)) and 1/pi folded in, in float64, rounded once
-		const double nn = (double)(1 - mm + 2 * k);
+	auto coef = [&](int d) -> double {
+		if (d < 0 || d >= nt) return 0.0;
+		// np.hanning(2nt+1)[nt + d] rounded to float32 (util/resampling.py:24,36), then the sign of
+		// sin(pi (d - s)) and 1/pi folded in
+		const double nn = (double)(1 - mm + 2 * (nt + d));
 		const float h = (float)(0.5 + 0.5 * cos(M_PI * nn / (double)(mm - 1)));
-		const int d = k - nt;
-		c[k] = (float)((((d + 1) & 1) ? -1.0 : 1.0) * (double)h / M_PI);
+		return (double)(float)((((d + 1) & 1) ? -1.0 : 1.0) * (double)h / M_PI);
+	};
+	t->c0 = (float)coef(0);
+	for (int p = 0; p < CAP; p++) {
+		const int d1 = 2 * p + 1, d2 = 2 * p + 2;
+		const double c1 = coef(d1), c2 = coef(d2);
+		if (p < SINC_NEAR_BLOCKS * (SINC_BLOCK / 2)) {
+			t->a[p] = make_float4(d1 < nt ? (float)((double)d1 * d1) : 1.f, d2 < nt ? (float)((double)d2 * d2) : 1.f,
+			                      (float)c1, (float)c2);
+			t->b[p] = make_float4((float)(c1 * d1), (float)(c2 * d2), (float)(-c1 * d1), (float)(-c2 * d2));
+		} else {
+			const double e1 = d1, e2 = d2;
+			t->a[p] = make_float4((float)(c1 / e1), (float)(c2 / e2), (float)(c1 / (e1 * e1 * e1)), (float)(c2 / (e2 * e2 * e2)));
+			t->b[p] = make_float4((float)(c1 / (e1 * e1)), (float)(c2 / (e2 * e2)), (float)(c1 / (e1 * e1 * e1 * e1)),
+			                      (float)(c2 / (e2 * e2 * e2 * e2)));
+		}
 	}
-	auto at = [&](int k) { return (k >= 0 && k < 2 * nt) ? c[k] : 0.f; };
-	auto lp = [&](int k) { return k == nt ? 0.f : at(k); };
-	for (int m = 0; m < CAP; m++) {
-		t->full[m] = make_float4(at(2 * m), at(2 * m + 1), at(2 * m - 1), at(2 * m));
-		t->lp[m] = make_float4(lp(2 * m), lp(2 * m + 1), lp(2 * m - 1), lp(2 * m));
-	}
-	return c[nt];
 }
 
 }  // namespace par

@@ -13,9 +13,11 @@ using namespace par;
 // Interior outputs only (all 2*NT taps inside the signal); edge outputs are written as NaN.
 extern "C" int sinc_emulate(const double *pos, long long m, const float *x, long long n_in, int nt, float *out) {
 	static SincTab<SINC_TAB_LARGE> tab;
-	const float centre = sinc_fill_table<SINC_TAB_LARGE>(nt, &tab);
-	std::vector<float> xp((size_t)n_in + 64, 0.f);
-	memcpy(xp.data() + 2, x, (size_t)n_in * sizeof(float));       // 2 floats of slack in front (O slot reads j0 = lo - 1)
+	sinc_fill_table<SINC_TAB_LARGE>(nt, &tab);
+	// parity planes of the zero-padded signal (sinc_core.cuh, "Staging layout"): staged sample P = input sample P - 16
+	const long long half = (n_in + 64) / 2 + 2;
+	std::vector<float> xp(2 * (size_t)half, 0.f);
+	for (long long j = 0; j < n_in; j++) { const long long P = j + 16; xp[(P & 1) * half + (P >> 1)] = x[j]; }
 	for (long long i = 0; i < m; i++) {
 		const double p = pos[i];
 		double per;
@@ -25,14 +27,18 @@ extern "C" int sinc_emulate(const double *pos, long long m, const float *x, long
 		if (!(su.cnt == 2 * nt && su.koff == 0)) { out[i] = NAN; continue; }
 		SincSlot dummy;
 		dummy.s = 0.5f; dummy.fc = 1.f; dummy.g_fx = 0; dummy.s_fx = 0;
-		const bool odd = su.lower & 1;
-		const long long j0 = su.lower & ~1ll;
-		const SincSlot &E = odd ? dummy : su.slot, &O = odd ? su.slot : dummy;
-		float yE[1], yO[1];
-		const float *xs = xp.data() + 2 + j0;
-		if (su.lowpass) sinc_unit<1, true>(nt, tab.lp, centre, xs, 0, E, O, yE, yO);
-		else sinc_unit<1, false>(nt, tab.full, centre, xs, 0, E, O, yE, yO);
-		out[i] = odd ? yO[0] : yE[0];
+		const long long cen = su.lower + nt + 16;            // staged index of the centre tap
+		const bool odd = cen & 1;
+		const long long c0 = cen & ~1ll;
+		const SincSlot &sE = odd ? dummy : su.slot, &sO = odd ? su.slot : dummy;
+		const unsigned long long gE = sE.g_fx, gO = sO.g_fx;
+		const long long fE = sE.s_fx, fO = sO.s_fx;
+		const SincSlotRef sl[2] = {{&sE.s, &sE.fc, &gE, &fE}, {&sO.s, &sO.fc, &gO, &fO}};
+		float y[2][1];
+		const SincWin<1> xs{xp.data() + (c0 >> 1), (int)half};
+		if (su.lowpass) sinc_unit<1, true, 2, SINC_TAB_LARGE>(nt, tab, xs, sl, y);
+		else sinc_unit<1, false, 2, SINC_TAB_LARGE>(nt, tab, xs, sl, y);
+		out[i] = y[odd ? 1 : 0][0];
 	}
 	return 0;
 }
