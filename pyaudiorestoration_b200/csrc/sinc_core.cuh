@@ -32,6 +32,13 @@
 #error "compile with nvcc (host emulation builds use nvcc's host pass)"
 #endif
 
+#ifndef SINC_BLOCK_UNROLL
+#define SINC_BLOCK_UNROLL 1
+#endif
+#ifndef SINC_EXACT_MASK
+#define SINC_EXACT_MASK 7           // fc < 1: exact block anchors at the far end and at every block b with (b & mask) == 0
+#endif
+
 namespace par {
 
 // ---- packed float32 pairs -------------------------------------------------------------------------
@@ -328,10 +335,12 @@ SC_HD void sinc_unit(int nt, const SincTab<CAP> &tab, const SincWin<CH> &x,
 		A[r].sar = A[r].sal = 0.f; A[r].car = 1.f; A[r].ncal = -1.f;
 		if (LOWPASS) rot[r].build(*sl[r].g_fx);
 	}
+	constexpr int kUnroll = SINC_BLOCK_UNROLL;
+#pragma unroll kUnroll
 	for (int b = nblk - 1; b >= 0; b--) {
 		if (LOWPASS) {
 			const int da = 8 * b + 1;
-			if (b == nblk - 1 || (b & 7) == 0) {
+			if (b == nblk - 1 || (b & SINC_EXACT_MASK) == 0) {
 #pragma unroll
 				for (int r = 0; r < R; r++) {
 					float cl;
