@@ -16,11 +16,20 @@ samples processed per second over all GPUs.
              its inputs host->device and its results device->host.
   roofline   the dominant kernel (the sinc interpolator), algorithmic bytes / CUDA-event time,
              against MEASURED_PEAKS.json; roofline_stft / roofline_positions give the other two.
+  parity     a sampled check of THIS run's device results against the CPU oracle: read positions bit
+             for bit, ~2*10^4 resampled outputs and a set of STFT frames to 1e-6.
+  competitor_torch_stft   the reference's own GPU back-end (util/fourier.py:92-121: torch.stft + /sqrt(N)
+             [+ .cpu()]) on the same input, device-resident and end to end.
+  strong_cfg3   BASELINE configs[2] (60 min, 8 ch, 192 kHz) as ONE job cut into N time chunks (strong
+             scaling; N = 1: the whole job on one GPU), device-generated input.
   cpu_baseline  the CPU oracle (port of the reference's numpy/numba path) on a bounded sample.
 
-Under torchrun (N > 1) every rank runs the same per-GPU workload on its own channels (weak
-scaling; --workload cfg3 shards the 8 channels of the 60-min config over the ranks instead); the
-only exchange is one NCCL broadcast of the speed curve and one gather of the output lengths.
+Under torchrun (N > 1) every rank runs the same per-GPU cfg2 workload on its own channels (weak scaling):
+rank 0 broadcasts the speed curve ONCE before the steps and the output lengths are gathered once after
+them -- the steps themselves need no communication.  `--impl reference` runs the UNMODIFIED reference
+(util/fourier.np_rfft_pick, util/resampling.speed_to_pos + sinc_wrapper_mt, copied to git-ignored
+baseline/_ref by scripts/install_reference.py) on the host cores; if that copy is missing it falls back
+to the oracle port and says so.
 """
 import argparse
 import json
@@ -44,6 +53,7 @@ WORKLOADS = {
 }
 METRIC = "audio samples/sec (STFT+varispeed resample)"
 UNIT = "samples/s"
+TOL = 1e-6
 
 
 # ------------------------------------------------------------------------------------ synthetic data
@@ -61,12 +71,32 @@ def synth_channel(n, sr, seed, out=None):
     return out
 
 
+def device_synth(torch, out, sr, seed, start=0):
+    """The same kind of signal generated on the device (cfg3 is 22 GB: host synthesis would take minutes):
+    `out` is a float32 (n,) device view holding samples start .. start + n of a channel."""
+    n = out.numel()
+    g = torch.Generator(device=out.device)
+    g.manual_seed(int(seed))
+    blk = 1 << 24
+    for s in range(0, n, blk):
+        e = min(n, s + blk)
+        t = (torch.arange(s, e, dtype=torch.float64, device=out.device) + float(start)) / float(sr)
+        v = 0.25 * torch.sin(2 * np.pi * 1000.0 * t) + 0.1 * torch.sin(2 * np.pi * (sr / 4.3) * t)
+        out[s:e] = v.to(torch.float32) + 0.05 * torch.randn(e - s, generator=g, device=out.device, dtype=torch.float32)
+    return out
+
+
 def wow_curve(duration, sr, hop=HOP, depth=0.01, freq=0.5556):
     """The speed curve as the GUI builds it (util/markers.py:585-599): K = int(duration*sr/hop)
     points on linspace(0, duration, K), +-1 % sinusoidal wow."""
     k = int(duration * sr / hop)
     times = np.linspace(0, duration, k)
     return np.stack((times, 1 + depth * np.sin(2 * np.pi * freq * times)), -1)
+
+
+def get_window():
+    import scipy.signal
+    return np.ascontiguousarray(scipy.signal.get_window("blackmanharris", N_FFT), dtype=np.float32)
 
 
 # ------------------------------------------------------------------------------------ clocks
@@ -135,11 +165,21 @@ def ncu_traffic(kernel):
         return None
 
 
-# ------------------------------------------------------------------------------------ CPU arm
-def cpu_pass(seconds, sr, seed, cores):
-    """One pass of the hot path on the host: the oracle's port of the reference's numpy STFT
-    (single-threaded per-frame rfft, util/fourier.py:136-157), speed_to_pos (:93-137) and
-    sinc_wrapper_mt (all cores, util/resampling.py:30-46) on `seconds` of one channel."""
+def workload_config(workload, world=1, channels_per_gpu=None, m=None):
+    """The `config` object of a line -- identical for the GPU arm and the reference arm of one workload."""
+    sr, dur, ch, desc = WORKLOADS[workload]
+    cfg = {"workload": f"{workload}: {desc}", "sample_rate": sr, "seconds": dur,
+           "channels_per_gpu": ch if channels_per_gpu is None else channels_per_gpu, "samples_per_channel": int(sr * dur),
+           "n_fft": N_FFT, "hop": HOP, "zeropad": 1, "window": "blackmanharris", "sinc_quality": NT,
+           "speed_curve": "1 + 0.01 sin(2 pi 0.5556 t), one point per hop"}
+    return cfg
+
+
+# ------------------------------------------------------------------------------------ CPU arms
+def cpu_pass_port(seconds, sr, seed, cores):
+    """One pass of the hot path on the host with the ORACLE PORT: numpy per-frame rfft STFT (single thread,
+    util/fourier.py:136-157), speed_to_pos (:93-137) and the float64 sinc with the reference's thread fan-out
+    (util/resampling.py:30-46) on `seconds` of one channel."""
     import oracle
     from oracle import oracle_np as onp
     n = int(seconds * sr)
@@ -156,11 +196,63 @@ def cpu_pass(seconds, sr, seed, cores):
     return n, (t1 - t0, t2 - t1, t3 - t2)
 
 
+_REF = None
+
+
+def reference_modules():
+    """The UNMODIFIED reference modules from baseline/_ref (scripts/install_reference.py), or None."""
+    global _REF
+    if _REF is None:
+        _REF = False
+        base = os.path.join(ROOT, "baseline", "_ref")
+        if os.path.exists(os.path.join(base, "util", "resampling.py")):
+            import importlib
+            import logging
+            import warnings
+            sys.path.insert(0, base)              # stays: numba resolves the jitted functions' globals through sys.modules
+            try:
+                logging.disable(logging.CRITICAL)
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    f = importlib.import_module("util.fourier")
+                    r = importlib.import_module("util.resampling")
+                if os.path.realpath(f.__file__).startswith(os.path.realpath(base)):
+                    _REF = (f, r)
+            except Exception as e:                                   # noqa: BLE001
+                print(f"reference import failed: {e!r}", file=sys.stderr)
+            finally:
+                logging.disable(logging.NOTSET)
+    return _REF or None
+
+
+def cpu_pass_reference(seconds, sr, seed, cores):
+    """The same pass with the reference's own functions: util.fourier.np_rfft_pick (its CPU back-end on this
+    image: pyfftw is not installed), util.resampling.speed_to_pos and sinc_wrapper_mt (numba, all cores)."""
+    import warnings
+    f, r = reference_modules()
+    n = int(seconds * sr)
+    x = synth_channel(n, sr, seed)
+    curve = wow_curve(seconds, sr)
+    win = get_window()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        t0 = time.perf_counter()
+        s = f.np_rfft_pick(N_FFT, HOP, win, x, 1)
+        t1 = time.perf_counter()
+        pos = r.speed_to_pos(curve[:, 0] * sr, curve[:, 1], n)
+        t2 = time.perf_counter()
+        out = np.empty((len(pos), 1), np.float32)
+        r.sinc_wrapper_mt(out[:, 0], pos, x, 0, NT)
+        t3 = time.perf_counter()
+    del s, out
+    return n, (t1 - t0, t2 - t1, t3 - t2)
+
+
 def cpu_baseline(sr, cores, budget_s=15.0):
-    n, (a, b, c) = cpu_pass(1.0, sr, 1234, cores)         # calibration (also warms caches / threads)
+    n, (a, b, c) = cpu_pass_port(1.0, sr, 1234, cores)         # calibration (also warms caches / threads)
     rate = n / (a + b + c)
     seconds = float(np.clip(budget_s * rate / sr, 2.0, 120.0))
-    n, (a, b, c) = cpu_pass(seconds, sr, 1234, cores)
+    n, (a, b, c) = cpu_pass_port(seconds, sr, 1234, cores)
     return {"value": n / (a + b + c), "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"first {seconds:.1f} s of channel 0 at {sr} Hz ({n} samples): numpy per-frame rfft STFT "
                       f"{a:.2f} s (1 thread) + speed_to_pos {b:.2f} s + float64 sinc NT={NT} {c:.2f} s ({cores} threads)",
@@ -168,133 +260,171 @@ def cpu_baseline(sr, cores, budget_s=15.0):
 
 
 def run_reference(args):
-    """--impl reference: the CPU implementation of the path (oracle port; the reference itself is
-    Python + numba and its sources may not travel to the GPU box) on the host cores."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     sr, dur, ch, desc = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
-    n, (a, b, c) = cpu_pass(1.0, sr, 1234, cores)
+    real = reference_modules() is not None
+    cpu_pass = cpu_pass_reference if real else cpu_pass_port
+    kind = "reference" if real else "port"
+    cpu_pass(1.0, sr, 1234, cores)                         # numba JIT / thread start-up outside every measurement
+    n, (a, b, c) = cpu_pass(2.0, sr, 1234, cores)
     rate = n / (a + b + c)
     seconds = float(np.clip(8.0 * rate / sr, 2.0, 60.0))   # ~8 s of CPU work per step
     for _ in range(args.warmup):
         cpu_pass(min(seconds, 2.0), sr, 1234, cores)
-    t0 = time.perf_counter()
-    total = 0
+    total, dt, parts = 0, 0.0, np.zeros(3)
     for _ in range(args.steps):
-        n, _ = cpu_pass(seconds, sr, 1234, cores)
+        n, t = cpu_pass(seconds, sr, 1234, cores)          # synthesis of the sample is outside the timed parts
         total += n
-    dt = time.perf_counter() - t0
-    # synthesis of the sample is outside the reference's path; re-time it and subtract
-    t1 = time.perf_counter()
-    for _ in range(args.steps):
-        synth_channel(int(seconds * sr), sr, 1234)
-        wow_curve(seconds, sr)
-    dt -= time.perf_counter() - t1
+        dt += sum(t)
+        parts += np.array(t)
     value = total / dt
-    sample = f"{seconds:.1f} s of one channel per step ({int(seconds * sr)} samples), oracle port, {cores} threads for the sinc stage"
+    what = ("unmodified reference (baseline/_ref): util.fourier.np_rfft_pick + util.resampling.speed_to_pos + "
+            "sinc_wrapper_mt (numba)") if real else "oracle port (baseline/_ref missing: run scripts/install_reference.py)"
+    sample = (f"{seconds:.1f} s of one channel per step ({int(seconds * sr)} samples): STFT {parts[0] / args.steps:.2f} s (1 thread) "
+              f"+ speed_to_pos {parts[1] / args.steps:.2f} s + sinc NT={NT} {parts[2] / args.steps:.2f} s ({cores} threads); {what}; "
+              "throughput is linear in samples, so it stands for the full workload")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 STFT / f64 sinc",
-            "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {desc}", "n_fft": N_FFT, "hop": HOP, "sinc_quality": NT},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "data": "synthetic", "config": workload_config(args.workload),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-# ------------------------------------------------------------------------------------ GPU arm, time shards
-def run_time_sharded(args, torch, dist, rank, world, local, dev):
-    """ONE job (all channels of the workload) cut into `world` time chunks: per step
-    one broadcast of the speed curve, one all-gather of the chunks' edge samples, then every rank
-    transforms the frames and resamples the outputs that fall into its chunk.  Strong scaling."""
+# ------------------------------------------------------------------------------------ sampled parity
+def sampled_parity(torch, x_dev, pos_dev, m, out_dev, S_dev, curve, sr, n, n_points=20000, n_frames=24, seed=0):
+    """Checks device results of one step against the CPU oracle WITHOUT computing the oracle for the whole job:
+    * read positions at `n_points` random output indices (+ their successors, + both ends) and the output count,
+      bit for bit against the serial float64 recurrence (oracle.speed_to_pos_at_c);
+    * the resampled value of every sampled interior output of every channel against the float64 sinc of the
+      oracle evaluated on the same 2*NT input samples (oracle.sinc_windows_c);
+    * `n_frames` STFT frames per channel against the float64 oracle transform of the same samples.
+    x_dev (C, n) float32, pos_dev (>= m) float64, out_dev (C, >= m) float32, S_dev (C, T, F) complex64 or None."""
+    import oracle
+    from oracle import oracle_np as onp
+    rng = np.random.default_rng(seed)
+    C = x_dev.shape[0]
+    st, sp = np.ascontiguousarray(curve[:, 0] * sr), np.ascontiguousarray(curve[:, 1])
+    pick = np.unique(np.concatenate([rng.integers(0, max(m - 1, 1), n_points), [0, 1, max(m - 2, 0)]]))
+    pick = pick[pick + 1 < m]
+    idx = np.unique(np.concatenate([pick, pick + 1, [m - 1]]))
+    want, m_ref = oracle.speed_to_pos_at_c(st, sp, n, idx)
+    dev = x_dev.device
+    got = pos_dev[torch.as_tensor(idx, device=dev)].cpu().numpy()
+    res = {"points": int(len(pick)), "tolerance": TOL, "output_count_equal": bool(m_ref == m),
+           "positions_bit_exact": bool(m_ref == m and np.array_equal(got, want))}
+    # sinc: interior outputs (all 2*NT taps inside the signal)
+    p = got[np.searchsorted(idx, pick)]
+    pn = got[np.searchsorted(idx, pick + 1)]
+    ind = np.rint(p).astype(np.int64)
+    base = ind - NT - 2
+    W = 2 * NT + 4
+    keep = (base >= 0) & (base + W <= n)
+    pick, p, pn, base = pick[keep], p[keep], pn[keep], base[keep]
+    gidx = torch.as_tensor(base[:, None] + np.arange(W)[None, :], device=dev)
+    pick_t = torch.as_tensor(pick, device=dev)
+    rel_l2, rel_max = 0.0, 0.0
+    for c in range(C):
+        wins = x_dev[c][gidx].cpu().numpy()
+        y = out_dev[c][pick_t].cpu().numpy().astype(np.float64)
+        ref = oracle.sinc_windows_c(p - base, pn - base, wins, NT).astype(np.float64)
+        rel_l2 = max(rel_l2, float(np.linalg.norm(y - ref) / max(np.linalg.norm(ref), 1e-300)))
+        rel_max = max(rel_max, float(np.max(np.abs(y - ref)) / max(np.max(np.abs(ref)), 1e-300)))
+    res.update(sinc_points=int(len(pick)) * C, sinc_rel_l2=rel_l2, sinc_rel_max=rel_max)
+    ok = res["positions_bit_exact"] and rel_l2 <= TOL and rel_max <= TOL
+    if S_dev is not None:
+        T = S_dev.shape[1]
+        j = N_FFT // (2 * HOP)                              # frame j of a lone n_fft-sample segment is centred on it
+        lo_t, hi_t = -(-(N_FFT // 2) // HOP), (n - N_FFT // 2) // HOP
+        frames = np.unique(rng.integers(lo_t, hi_t + 1, n_frames))
+        seg_idx = torch.as_tensor((frames * HOP - N_FFT // 2)[:, None] + np.arange(N_FFT)[None, :], device=dev)
+        worst = 0.0
+        for c in range(C):
+            segs = x_dev[c][seg_idx].cpu().numpy()
+            got_f = S_dev[c][torch.as_tensor(frames, device=dev)].cpu().numpy().astype(np.complex128)
+            for k in range(len(frames)):
+                ref_f = onp.stft_f64(segs[k], N_FFT, HOP)[j]
+                worst = max(worst, float(np.linalg.norm(got_f[k] - ref_f) / max(np.linalg.norm(ref_f), 1e-300)))
+        res.update(stft_frames=int(len(frames)) * C, stft_rel_l2=worst, stft_frame_count=int(T))
+        ok = ok and worst <= TOL
+    res["pass"] = bool(ok)
+    return res
+
+
+# ------------------------------------------------------------------------------------ cfg3, strong scaling
+def run_cfg3_strong(torch, dist, rank, world, dev, steps, workload="cfg3"):
+    """ONE job (all channels of the workload) cut into `world` time chunks: the speed curve is
+    broadcast once, then per step one all-gather of the chunks' edge samples, one all-gather of the per-segment
+    totals of the curve, and every rank transforms the frames and resamples the outputs that fall into its chunk.
+    Input is generated on the device.  Returns the record on rank 0 (None elsewhere)."""
     from pyaudiorestoration_b200 import _lib, dist as pdist
     L = _lib.lib()
-    sr, dur, C, desc = WORKLOADS[args.workload]
+    sr, dur, C, desc = WORKLOADS[workload]
     n = int(sr * dur)
     sh = pdist.TimeShard(n, N_FFT, HOP, NT, rank, world)
-    ln = sh.s1 - sh.s0
-    host_chunk = _lib.pinned_empty((C, ln), np.float32)
-    for c in range(C):
-        synth_channel(ln, sr, 1234 + c + 100 * rank, out=host_chunk[c])
     buf = sh.local_buffer(C, dev)
-    sh.chunk_view(buf).copy_(torch.from_numpy(host_chunk))
+    chunk = sh.chunk_view(buf)
+    for c in range(C):
+        device_synth(torch, chunk[c], sr, 1234 + c, start=sh.s0)
     curve = wow_curve(dur, sr) if rank == 0 else None
-    window = np.ascontiguousarray(__import__("scipy.signal").signal.get_window("blackmanharris", N_FFT), dtype=np.float32)
+    cv = pdist.broadcast_curve(curve, src=0, device=dev)           # once per job: the curve is an input like the audio
+    st, sp = np.ascontiguousarray(cv[:, 0] * sr), np.ascontiguousarray(cv[:, 1])
+    window = get_window()
     nfr, F = sh.frame1 - sh.frame0, N_FFT // 2 + 1
     S_out = torch.empty((C, nfr, F), dtype=torch.complex64, device=dev)
-    pos_buf = torch.empty(int(ln * 1.1) + 8 * HOP, dtype=torch.float64, device=dev)
+    pos_buf = torch.empty(int((sh.s1 - sh.s0) * 1.1) + 8 * HOP, dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream(dev)
 
-    def step(upload=False):
-        if upload:                                   # e2e: this step's audio comes from (pinned) host memory
-            sh.chunk_view(buf).copy_(torch.from_numpy(host_chunk), non_blocking=True)
-        cv = pdist.broadcast_curve(curve, src=0, device=dev)
+    def step():
         sh.exchange_halos(buf)
         sh.stft(buf, window, out=S_out)
-        ps, p0, m = sh.positions(cv[:, 0] * sr, cv[:, 1], dev, out=pos_buf)
+        ps, p0, m = sh.positions(st, sp, dev, out=pos_buf)
         y = sh.resample(buf, ps, "Sinc", pos_origin=p0, m=m)
         return y, m
 
     def barrier():
-        dist.barrier()
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(max(args.warmup, 3)):
-        step()
+    for _ in range(3):
+        y, m = step()
+        del y
     barrier()
     launches0 = L.par_kernel_launch_count()
-    clocks = ClockSampler(local)
-    clocks.start()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         y, m = step()
+        del y
     t1.record(stream)
     barrier()
-    tm = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
-    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    ms = float(tm.item())
-    clk = clocks.stop()
+    ms = t0.elapsed_time(t1)
+    if world > 1:
+        tm = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ms = float(tm.item())
     launches = L.par_kernel_launch_count() - launches0
-    # e2e: host chunk in, spectrogram + resampled audio back in pinned host memory
-    S_host = torch.empty(S_out.shape, dtype=S_out.dtype).pin_memory()
-    y_host = torch.empty((C, int(ln * 1.1) + 8 * HOP), dtype=torch.float32).pin_memory()
-    e_steps = max(2, min(args.steps, 5))
-
-    def e2e_step():
-        y, m = step(upload=True)
-        S_host.copy_(S_out, non_blocking=True)
-        y_host[:, :y.shape[1]].copy_(y, non_blocking=True)
-        torch.cuda.synchronize(dev)
-        return y.shape[1]
-    e2e_step()
-    barrier()
-    w0 = time.perf_counter()
-    for _ in range(e_steps):
-        mine = e2e_step()
-    dt = torch.tensor([time.perf_counter() - w0], dtype=torch.float64, device=dev)
-    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    rec = None
     if rank == 0:
-        line = {
-            "metric": METRIC, "value": n * C * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32 (positions f64)", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {desc}", "sample_rate": sr, "seconds": dur, "channels": C,
-                       "samples_per_channel": n, "n_fft": N_FFT, "hop": HOP, "sinc_quality": NT,
-                       "parallelism": f"time chunks x{world}, halo {sh.H} samples, 1 all-gather of edge blocks + 1 curve "
-                                      f"broadcast per step",
-                       "l2": "per-rank inputs and outputs exceed the 126 MB L2; no flush"},
-            "e2e": {"value": n * C * e_steps / float(dt.item()), "unit": UNIT,
-                    "h2d_bytes_per_step": int(C * ln * 4), "d2h_bytes_per_step": int(C * nfr * F * 8 + C * mine * 4),
-                    "steps": e_steps, "ms_per_step": float(dt.item()) / e_steps * 1e3,
-                    "api": "per rank: pinned host chunk -> TimeShard.exchange_halos/stft/positions/resample -> pinned host"},
-            "gpu_launches": int(launches), "clocks": clk, "roofline": None, "cpu_baseline": None,
-        }
-        print(json.dumps(line), flush=True)
+        rec = {"workload": f"{workload}: {desc}", "scaling": "strong", "n_gpus": world, "steps": steps,
+               "ms_per_step": ms / steps, "value": n * C * steps / (ms * 1e-3), "unit": UNIT,
+               "channels": C, "samples_per_channel": n, "output_samples_per_channel": int(m),
+               "gpu_launches": int(launches),
+               "parallelism": (f"time chunks x{world}, halo {sh.H} samples: per step 1 all-gather of edge blocks + 1 all-gather of "
+                               f"{len(st) - 1} segment totals; curve broadcast once per job") if world > 1 else "1 GPU, whole job",
+               "note": "speed-up vs 1 GPU = this ms_per_step against strong_cfg3.ms_per_step of the N=1 line"}
+    del buf, S_out, pos_buf
+    torch.cuda.empty_cache()
+    L.par_release_cached_memory(dev.index)
+    return rec
 
 
 # ------------------------------------------------------------------------------------ GPU arm
@@ -305,11 +435,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--shard", default="channels", choices=["channels", "time"],
-                    help="N > 1: every rank its own channels (weak scaling, default) or one job cut into time chunks "
-                         "with a boundary all-gather (strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-competitor", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the cfg3 strong-scaling record")
+    ap.add_argument("--strong-steps", type=int, default=5)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -334,11 +465,6 @@ def main():
     L = _lib.lib()
     _lib.require_device()
 
-    if args.shard == "time" and world > 1:
-        run_time_sharded(args, torch, dist, rank, world, local, dev)
-        dist.destroy_process_group()
-        return
-
     sr, dur, ch_total, desc = WORKLOADS[args.workload]
     if args.workload == "cfg3":
         if ch_total % world:
@@ -361,9 +487,14 @@ def main():
         synth_channel(n, sr, 1234 + c, out=tmp_ch)
         host_sig[:, i] = tmp_ch
     del tmp_ch
-    curve = wow_curve(dur, sr)
-    curve_t = torch.from_numpy(curve.copy()).to(dev)
-    window = np.ascontiguousarray(__import__("scipy.signal").signal.get_window("blackmanharris", N_FFT), dtype=np.float32)
+    # the speed curve comes from rank 0: ONE broadcast per job, before the steps
+    curve = wow_curve(dur, sr) if rank == 0 else None
+    if world > 1:
+        from pyaudiorestoration_b200 import dist as pdist
+        curve = pdist.broadcast_curve(curve, src=0, device=dev)
+    st = np.ascontiguousarray(curve[:, 0] * sr)
+    sp = np.ascontiguousarray(curve[:, 1])
+    window = get_window()
     x_dev = torch.from_numpy(host_sig).to(dev).t().contiguous()
     S_dev = torch.empty((C, T, F), dtype=torch.complex64, device=dev)
     cap = int(n * 1.02) + 4096
@@ -372,16 +503,10 @@ def main():
     stream = torch.cuda.current_stream(dev)
     sh = stream.cuda_stream
     m_box = np.zeros(1, np.int64)
-    lens = torch.zeros(world, dtype=torch.int64, device=dev)
     ev = {k: [] for k in ("stft", "pos", "sinc")}
 
     def step(timed):
         """One device-resident pass.  Returns the number of output samples."""
-        if world > 1:
-            dist.broadcast(curve_t, 0)            # the speed curve comes from rank 0 (SURVEY.md 8e)
-        cv = curve_t.cpu().numpy() if world > 1 else curve
-        st = np.ascontiguousarray(cv[:, 0] * sr)
-        sp = np.ascontiguousarray(cv[:, 1])
         e = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timed else None
         if timed:
             e[0].record(stream)
@@ -402,9 +527,6 @@ def main():
             ev["stft"].append((e[0], e[1]))
             ev["pos"].append((e[1], e[2]))
             ev["sinc"].append((e[2], e[3]))
-        if world > 1:
-            mine = torch.tensor([m], dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(lens, mine)
         return m
 
     def barrier():
@@ -428,10 +550,14 @@ def main():
     ms = t_start.elapsed_time(t_end)
     clk = clocks.stop()
     launches = L.par_kernel_launch_count() - launches0
+    lens = None
     if world > 1:
         tm = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         ms = float(tm.item())
+        lens = torch.zeros(world, dtype=torch.int64, device=dev)      # one gather of the output lengths per job
+        dist.all_gather_into_tensor(lens, torch.tensor([m], dtype=torch.int64, device=dev))
+        lens = [int(v) for v in lens.tolist()]
     samples_per_step = n * C * world if scaling == "weak" else n * ch_total
     value = samples_per_step * args.steps / (ms * 1e-3)
 
@@ -451,6 +577,67 @@ def main():
         if extra:
             r.update(extra)
         return r
+
+    # ---- parity of THIS run's device results (sampled), rank 0
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = sampled_parity(torch, x_dev, pos_dev, m, out_dev, S_dev, curve, sr, n)
+
+    # ---- the reference's own GPU back-end on the same input (util/fourier.py:92-121), rank 0
+    competitor = None
+    if rank == 0 and not args.no_competitor:
+        win_t = torch.from_numpy(window).to(dev)
+
+        def torch_stft_dev():
+            out = []
+            for c in range(C):
+                s_ = torch.stft(x_dev[c], N_FFT, hop_length=HOP, window=win_t, win_length=N_FFT, center=True,
+                                pad_mode="reflect", normalized=False, onesided=True, return_complex=True)
+                s_ /= np.sqrt(N_FFT)
+                out.append(s_)
+            return out
+
+        def timeit(fn, reps):
+            fn()
+            torch.cuda.synchronize(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(reps):
+                r_ = fn()
+                del r_
+            b.record(stream)
+            torch.cuda.synchronize(dev)
+            return a.elapsed_time(b) / reps
+        dev_ms = timeit(torch_stft_dev, 5)
+
+        def torch_stft_e2e():                       # torch_rfft2 as written: host array in, .cpu() tensor out, per channel
+            out = []
+            for c in range(C):
+                xs_ = torch.from_numpy(np.ascontiguousarray(host_sig[:, c])).to(dev)
+                s_ = torch.stft(xs_, N_FFT, hop_length=HOP, window=win_t, win_length=N_FFT, center=True, pad_mode="reflect",
+                                normalized=False, onesided=True, return_complex=True)
+                s_ /= np.sqrt(N_FFT)
+                out.append(s_.cpu())
+            return out
+        torch_stft_e2e()
+        t0 = time.perf_counter()
+        r_ = torch_stft_e2e()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        del r_
+
+        def ours_e2e():
+            return [fourier.stft(host_sig[:, c], N_FFT, HOP) for c in range(C)]
+        ours_e2e()
+        t0 = time.perf_counter()
+        r_ = ours_e2e()
+        ours_ms = (time.perf_counter() - t0) * 1e3
+        del r_
+        competitor = {"what": "torch.stft (cuFFT) with the reference's arguments + /sqrt(n_fft), util/fourier.py:92-121",
+                      "device_ms": dev_ms, "ours_device_ms": k_stft, "device_speedup": dev_ms / k_stft,
+                      "e2e_ms": e2e_ms, "ours_e2e_ms": ours_ms, "e2e_speedup": e2e_ms / ours_ms,
+                      "e2e_note": "host float32 column in, host complex64 (F, T) out, per channel, pageable .cpu() result vs "
+                                  "this repo's util.fourier.stft"}
+        torch.cuda.empty_cache()
 
     # ---- e2e through the reference-facing API (host buffers in, host arrays out)
     e2e = None
@@ -490,24 +677,37 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(sr, os.cpu_count() or 1)
 
+    # ---- BASELINE configs[2] as one strong-scaling job on the same ranks
+    strong = None
+    if not args.no_strong and args.workload == "cfg2":
+        del x_dev, S_dev, pos_dev, out_dev
+        torch.cuda.empty_cache()
+        L.par_release_cached_memory(local)
+        try:
+            strong = run_cfg3_strong(torch, dist, rank, world, dev, args.strong_steps)
+        except Exception as e:                                                   # noqa: BLE001
+            if world > 1:
+                raise
+            strong = {"error": repr(e)}
+
     if rank == 0:
+        cfg = workload_config(args.workload, world, C, m)
+        cfg.update({"output_samples_per_channel": m,
+                    "l2": "inputs (%.0f MB) and outputs (%.0f MB) per step exceed the 126 MB L2; no flush" % (
+                        C * n * 4 / 1e6, (C * T * F * 8 + C * m * 4 + m * 8) / 1e6),
+                    "parallelism": (f"channels x{world}: every rank its own {C} channels; curve broadcast once before, output "
+                                    f"lengths gathered once after the steps") if world > 1 else "1 GPU"})
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f32 (positions f64)", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {desc}", "sample_rate": sr, "seconds": dur,
-                       "channels_per_gpu": C, "samples_per_channel": n, "n_fft": N_FFT, "hop": HOP, "zeropad": 1,
-                       "window": "blackmanharris", "sinc_quality": NT, "output_samples_per_channel": m,
-                       "speed_curve": "1 + 0.01 sin(2 pi 0.5556 t), one point per hop",
-                       "l2": "inputs (%.0f MB) and outputs (%.0f MB) per step exceed the 126 MB L2; no flush" % (
-                           C * n * 4 / 1e6, (C * T * F * 8 + C * m * 4 + m * 8) / 1e6),
-                       "parallelism": f"channels x{world}" if world > 1 else "1 GPU"},
+            "config": cfg,
             "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": roof(bytes_sinc, k_sinc, "sinc_kernel",
-                             {"note": "sinc stage is FP32-issue/MUFU bound (2*NT reciprocals per output sample), "
-                                      "not HBM bound; see DESIGN.md",
+                             {"note": "sinc stage is FP32-pipe bound (4.5 / 7.5 FMA-pipe operations per tap at fc = 1 / fc < 1 for "
+                                      "2 channels), not HBM bound; see DESIGN.md",
                               "taps_per_s": C * m * 2 * NT / (k_sinc * 1e-3)}),
             "roofline_stft": roof(bytes_stft, k_stft, "stft_kernel",
                                   {"note": "stft_tma_kernel<11,0>: TMA-staged frames, HBM-bound by design"}),
@@ -515,6 +715,10 @@ def main():
                                        {"note": "stage time includes the serial host chain of speed_to_pos (2 stream "
                                                 "synchronisations); kernels: expand_positions + add_offsets"}),
             "stage_ms": {"stft": k_stft, "positions": k_pos, "sinc": k_sinc},
+            "parity": parity,
+            "competitor_torch_stft": competitor,
+            "strong_cfg3": strong,
+            "output_lengths": lens,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

@@ -37,6 +37,10 @@ def lib():
         L.oracle_sinc_mt.restype = ctypes.c_int
         L.oracle_speed_to_pos.argtypes = [dp, dp, i64, ctypes.c_double, dp, i64]
         L.oracle_speed_to_pos.restype = i64
+        L.oracle_speed_to_pos_at.argtypes = [dp, dp, i64, ctypes.c_double, dp, i64, dp]
+        L.oracle_speed_to_pos_at.restype = i64
+        L.oracle_sinc_windows.argtypes = [dp, dp, i64, fp, i64, ctypes.c_int, fp, fp]
+        L.oracle_sinc_windows.restype = None
         _LIB = L
     return _LIB
 
@@ -71,3 +75,30 @@ def speed_to_pos_c(sampletimes, speeds, num_input_samples):
     if n < 0:
         raise RuntimeError("oracle_speed_to_pos: capacity exceeded")
     return out[:n].copy()
+
+
+def speed_to_pos_at_c(sampletimes, speeds, num_input_samples, idx):
+    """The positions util/resampling.py:93-137 would return at the ascending output indices ``idx`` (NaN past the
+    end), and the total number of valid positions -- without materialising the whole array."""
+    st = np.ascontiguousarray(sampletimes, dtype=np.float64)
+    sp = np.ascontiguousarray(speeds, dtype=np.float64)
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    if len(idx) > 1 and np.any(np.diff(idx) < 0):
+        raise ValueError("idx must ascend")
+    out = np.empty(len(idx), dtype=np.float64)
+    m = lib().oracle_speed_to_pos_at(st.ctypes.data, sp.ctypes.data, len(sp), float(num_input_samples),
+                                     idx.ctypes.data, len(idx), out.ctypes.data)
+    return out, int(m)
+
+
+def sinc_windows_c(p, pnext, windows, nt):
+    """util/resampling.py:51-90 for isolated outputs: row j of ``windows`` holds the input samples around output j,
+    ``p[j]`` / ``pnext[j]`` its read position and the next one, relative to the row's first sample."""
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    pnext = np.ascontiguousarray(pnext, dtype=np.float64)
+    windows = np.ascontiguousarray(windows, dtype=np.float32)
+    win = np.hanning(2 * nt + 1).astype(np.float32)
+    out = np.empty(len(p), dtype=np.float32)
+    lib().oracle_sinc_windows(p.ctypes.data, pnext.ctypes.data, len(p), windows.ctypes.data, windows.shape[1], int(nt),
+                              win.ctypes.data, out.ctypes.data)
+    return out

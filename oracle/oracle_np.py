@@ -354,15 +354,17 @@ def max_mono_ref(signal, fft_size, hop):
 
 
 def heuristic_peaks_ref(magnitude, sr, fft_size, f_lower, f_upper, num_bands):
-    """Per-band integer peak lists of dropouts_gui.py:251, :264-288, top band first."""
+    """Per-band integer peak lists of dropouts_gui.py:251, :264-288, top band first.  Band edges are converted
+    to ``int`` before the multiplication (numpy 1.x promotion; under numpy 2 the reference's ``uint16 * int``
+    wraps and every band is empty -- see tests/golden/make_golden_dropouts_full.py)."""
     import scipy.signal
     imdata = 20 * np.log10(np.array(magnitude))
     bands = np.logspace(np.log2(f_lower), np.log2(f_upper), num=num_bands, endpoint=True, base=2, dtype=np.uint16)
     pairs = list(zip(bands[:-1], bands[1:]))
     out = []
     for f_lower_band, f_upper_band in reversed(pairs):
-        bin_lower = int(f_lower_band * fft_size / sr)
-        bin_upper = int(f_upper_band * fft_size / sr)
+        bin_lower = int(int(f_lower_band) * fft_size / sr)
+        bin_upper = int(int(f_upper_band) * fft_size / sr)
         vol = np.mean(imdata[bin_lower:bin_upper], axis=0)
         peaks, _ = scipy.signal.find_peaks(-vol, prominence=5, rel_height=0.5)
         out.append(peaks)

@@ -605,9 +605,30 @@ PAR_API int par_speed_segments(const double *sampletimes, const double *speeds, 
 	return PAR_OK;
 }
 
+// Pinned staging memory for the small per-call arrays of speed_to_pos (segment tables up, segment sums
+// down): one growing buffer per host thread, so the copies run at full PCIe rate and without the driver's
+// pageable-memory bounce.  The owning call synchronises its stream before returning, so the buffer is free
+// for the thread's next call.
+struct PinnedScratch {
+	char *p = nullptr;
+	size_t cap = 0;
+	~PinnedScratch() { if (p) cudaFreeHost(p); }
+	char *get(size_t bytes) {
+		if (bytes > cap) {
+			if (p) cudaFreeHost(p);
+			p = nullptr; cap = 0;
+			size_t want = bytes + bytes / 4 + 4096;
+			if (cudaHostAlloc((void **)&p, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); p = nullptr; return nullptr; }
+			cap = want;
+		}
+		return p;
+	}
+};
+static thread_local PinnedScratch g_pinned;
+
 // Speed curve -> device-resident read positions.  `pos` must hold `cap` doubles on the device;
-// *m_out receives the number of valid positions.  Synchronises `st` once (the per-segment sums
-// have to reach the host for the serial offset chain and the end test, util/resampling.py:125-135).
+// *m_out receives the number of valid positions.  Synchronises `st` (the per-segment sums have to reach
+// the host for the serial offset chain and the end test, util/resampling.py:125-135).
 struct SegChain {                 // host copy of the serial part of speed_to_pos
 	std::vector<int64_t> start;   // first output index of every segment
 	std::vector<double> off;      // carried offset = position just before the segment's first output
@@ -617,47 +638,58 @@ static int positions_device(const double *sampletimes, const double *speeds, int
                             const std::vector<int64_t> &seg_n, int64_t total, double *pos, int64_t cap,
                             int64_t *m_out, cudaStream_t st, SegChain *chain = nullptr,
                             const double *window = nullptr, int64_t *win_origin = nullptr,
-                            int64_t *win_count = nullptr) {
+                            int64_t *win_count = nullptr, const double *ext_sums_dev = nullptr) {
 	// window = {lo, hi}: expand only the segments that hold positions in [lo, hi] (plus the segment
-	// after them, for the period of the last output); pos[0] is then output *win_origin
+	// after them, for the period of the last output); pos[0] is then output *win_origin.
+	// ext_sums_dev: the per-segment totals of the whole curve, already on the device (ranks of a time-sharded
+	// job compute a slice each and all-gather them): nothing but the window's segments is uploaded then.
 	int rc;
 	const int64_t n_seg = k - 1;
-	std::vector<int64_t> seg_start(n_seg);
+	const bool one_pass = !window && cap >= total && !ext_sums_dev;
+	// pinned layout: [speeds k][seg_n n_seg][seg_start n_seg][sums n_seg][off n_seg]
+	const size_t bytes = ((size_t)k + 4 * (size_t)n_seg) * 8;
+	char *pin = g_pinned.get(bytes);
+	if (!pin) { set_error("speed_to_pos: pinned staging allocation failed"); return PAR_ECUDA; }
+	double *h_sp = (double *)pin;
+	int64_t *h_n = (int64_t *)(h_sp + k);
+	int64_t *h_start = h_n + n_seg;
+	double *h_sums = (double *)(h_start + n_seg);
+	double *h_off = h_sums + n_seg;
+	memcpy(h_sp, speeds, (size_t)k * 8);
 	int64_t o = 0;
-	for (int64_t i = 0; i < n_seg; i++) { seg_start[i] = o; if (seg_n[i] > 0) o += seg_n[i]; }
+	for (int64_t i = 0; i < n_seg; i++) { h_n[i] = seg_n[i]; h_start[i] = o; if (seg_n[i] > 0) o += seg_n[i]; }
 
-	DevBuf d_sp(st), d_n(st), d_sum(st), d_start(st), d_off(st);
-	if ((rc = d_sp.alloc(k * sizeof(double))) != PAR_OK) return rc;
-	if ((rc = d_n.alloc(n_seg * sizeof(int64_t))) != PAR_OK) return rc;
-	if ((rc = d_sum.alloc(n_seg * sizeof(double))) != PAR_OK) return rc;
-	if ((rc = d_start.alloc(n_seg * sizeof(int64_t))) != PAR_OK) return rc;
-	if ((rc = d_off.alloc(n_seg * sizeof(double))) != PAR_OK) return rc;
-	PAR_CUDA(cudaMemcpyAsync(d_sp.p, speeds, k * sizeof(double), cudaMemcpyHostToDevice, st));
-	PAR_CUDA(cudaMemcpyAsync(d_n.p, seg_n.data(), n_seg * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-	PAR_CUDA(cudaMemcpyAsync(d_start.p, seg_start.data(), n_seg * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-	// whole-curve call: ONE pass writes every segment's bare cumsum into pos (capacity permitting) and
-	// its total; after the host chain a streaming pass adds the offsets.  Windowed call (shards):
-	// totals only, then expand just the window's segments.
-	const bool one_pass = !window && cap >= total;
-	if (one_pass)
-		rc = launch_expand_positions(d_sp.as<double>(), d_n.as<int64_t>(), d_start.as<int64_t>(), nullptr, n_seg, pos,
-		                             total, st, d_sum.as<double>());
-	else
-		rc = launch_segment_sums(d_sp.as<double>(), d_n.as<int64_t>(), n_seg, d_sum.as<double>(), st);
-	if (rc != PAR_OK) return rc;
-	std::vector<double> sums(n_seg), off(n_seg);
-	PAR_CUDA(cudaMemcpyAsync(sums.data(), d_sum.p, n_seg * sizeof(double), cudaMemcpyDeviceToHost, st));
+	DevBuf d_tab(st), d_sum(st), d_off(st);
+	double *d_sp = nullptr;
+	int64_t *d_n = nullptr, *d_start = nullptr;
+	if (!ext_sums_dev) {
+		if ((rc = d_tab.alloc(((size_t)k + 2 * (size_t)n_seg) * 8)) != PAR_OK) return rc;
+		if ((rc = d_sum.alloc((size_t)n_seg * 8)) != PAR_OK) return rc;
+		d_sp = d_tab.as<double>();
+		d_n = (int64_t *)(d_sp + k);
+		d_start = d_n + n_seg;
+		PAR_CUDA(cudaMemcpyAsync(d_sp, h_sp, ((size_t)k + 2 * (size_t)n_seg) * 8, cudaMemcpyHostToDevice, st));
+		// whole-curve call: ONE pass writes every segment's bare cumsum into pos (capacity permitting) and
+		// its total; after the host chain a streaming pass adds the offsets.  Windowed call: totals only,
+		// then expand just the window's segments.
+		if (one_pass) rc = launch_expand_positions(d_sp, d_n, d_start, nullptr, n_seg, pos, total, st, d_sum.as<double>());
+		else rc = launch_segment_sums(d_sp, d_n, n_seg, d_sum.as<double>(), st);
+		if (rc != PAR_OK) return rc;
+		PAR_CUDA(cudaMemcpyAsync(h_sums, d_sum.p, (size_t)n_seg * 8, cudaMemcpyDeviceToHost, st));
+	} else {
+		PAR_CUDA(cudaMemcpyAsync(h_sums, ext_sums_dev, (size_t)n_seg * 8, cudaMemcpyDeviceToHost, st));
+	}
 	PAR_CUDA(cudaStreamSynchronize(st));
 
 	// serial offset chain + end test (util/resampling.py:125-135): one addition per segment; the
 	// division for the block's first position is only needed once the end test can fire
 	double offset = sampletimes[0];
-	int64_t m = total;
+	int64_t m = total, last_seg = n_seg;        // last_seg: first segment the reference never reaches
 	for (int64_t i = 0; i < n_seg; i++) {
-		off[i] = offset;
+		h_off[i] = offset;
 		const int64_t n = seg_n[i];
 		if (n <= 0) continue;                   // the reference raises on an empty block
-		const double last = sums[i] + offset;
+		const double last = h_sums[i] + offset;
 		if (num_input_samples <= last) {
 			double inv0 = 1.0 / speeds[i];
 			if (n == 1) inv0 = NAN;               // arange(1)/0 -> nan in the reference
@@ -678,22 +710,25 @@ static int positions_device(const double *sampletimes, const double *speeds, int
 					const double dist = fabs(pj - num_input_samples);
 					if (dist < best) { best = dist; besti = j; }
 				}
-				m = seg_start[i] + besti;
+				m = h_start[i] + besti;
+				last_seg = i + 1;
 				break;
 			}
 		}
 		offset = last;
 	}
+	// segments behind the end of the file hold no positions: they must not look like "below the window"
+	for (int64_t i = last_seg; i < n_seg; i++) h_off[i] = INFINITY;
 	*m_out = m;
 	int64_t seg_a = 0, seg_b = n_seg;          // segments [seg_a, seg_b) are expanded
 	if (window) {
 		// off[i] = position just before segment i's first output; positions grow with i for positive speeds
-		while (seg_a + 1 < n_seg && off[seg_a + 1] < window[0]) seg_a++;
+		while (seg_a + 1 < last_seg && h_off[seg_a + 1] < window[0]) seg_a++;
 		seg_b = seg_a;
-		while (seg_b < n_seg && off[seg_b] <= window[1]) seg_b++;
-		if (seg_b < n_seg) seg_b++;
-		const int64_t o_begin = seg_start[seg_a] < m ? seg_start[seg_a] : m;
-		const int64_t o_end = seg_b < n_seg ? (seg_start[seg_b] < m ? seg_start[seg_b] : m) : m;
+		while (seg_b < last_seg && h_off[seg_b] <= window[1]) seg_b++;
+		if (seg_b < last_seg) seg_b++;
+		const int64_t o_begin = h_start[seg_a] < m ? h_start[seg_a] : m;
+		const int64_t o_end = seg_b < n_seg ? (h_start[seg_b] < m ? h_start[seg_b] : m) : m;
 		*win_origin = o_begin;
 		*win_count = o_end - o_begin;
 		if (*win_count > cap) {
@@ -707,15 +742,31 @@ static int positions_device(const double *sampletimes, const double *speeds, int
 		return PAR_ECAPACITY;
 	}
 	if (m == 0) return PAR_OK;
-	if (chain) { chain->start = seg_start; chain->off = off; }
-	PAR_CUDA(cudaMemcpyAsync(d_off.p, off.data(), n_seg * sizeof(double), cudaMemcpyHostToDevice, st));
-	if (one_pass)
-		rc = launch_add_offsets(d_n.as<int64_t>(), d_start.as<int64_t>(), d_off.as<double>(), n_seg, pos, m, st);
-	else
-		rc = launch_expand_positions(d_sp.as<double>() + seg_a, d_n.as<int64_t>() + seg_a, d_start.as<int64_t>() + seg_a,
-		                             d_off.as<double>() + seg_a, seg_b - seg_a, pos, m, st);
+	if (chain) {
+		chain->start.assign(h_start, h_start + n_seg);
+		chain->off.assign(h_off, h_off + n_seg);
+	}
+	const int64_t cnt = seg_b - seg_a;
+	if (ext_sums_dev) {
+		// upload just the window's rows of the segment tables: [speeds cnt+1][seg_n cnt][seg_start cnt][off cnt]
+		if ((rc = d_tab.alloc(((size_t)cnt * 4 + 1) * 8)) != PAR_OK) return rc;
+		d_sp = d_tab.as<double>();
+		d_n = (int64_t *)(d_sp + cnt + 1);
+		d_start = d_n + cnt;
+		double *d_o = (double *)(d_start + cnt);
+		PAR_CUDA(cudaMemcpyAsync(d_sp, h_sp + seg_a, (size_t)(cnt + 1) * 8, cudaMemcpyHostToDevice, st));
+		PAR_CUDA(cudaMemcpyAsync(d_n, h_n + seg_a, (size_t)cnt * 8, cudaMemcpyHostToDevice, st));
+		PAR_CUDA(cudaMemcpyAsync(d_start, h_start + seg_a, (size_t)cnt * 8, cudaMemcpyHostToDevice, st));
+		PAR_CUDA(cudaMemcpyAsync(d_o, h_off + seg_a, (size_t)cnt * 8, cudaMemcpyHostToDevice, st));
+		rc = launch_expand_positions(d_sp, d_n, d_start, d_o, cnt, pos, m, st);
+	} else {
+		if ((rc = d_off.alloc((size_t)cnt * 8)) != PAR_OK) return rc;
+		PAR_CUDA(cudaMemcpyAsync(d_off.p, h_off + seg_a, (size_t)cnt * 8, cudaMemcpyHostToDevice, st));
+		if (one_pass) rc = launch_add_offsets(d_n, d_start, d_off.as<double>(), n_seg, pos, m, st);
+		else rc = launch_expand_positions(d_sp + seg_a, d_n + seg_a, d_start + seg_a, d_off.as<double>(), cnt, pos, m, st);
+	}
 	if (rc != PAR_OK) return rc;
-	// `off` (pageable) must outlive its async copy
+	// the pinned staging buffer must outlive its async copies
 	PAR_CUDA(cudaStreamSynchronize(st));
 	return PAR_OK;
 }
@@ -764,6 +815,59 @@ extern "C" PAR_API int par_speed_to_pos_range_f64(const double *sampletimes, con
 	const double window[2] = {lo_pos, hi_pos};
 	return positions_device(sampletimes, speeds, k, num_input_samples, seg_n, total, pos, cap, m, (cudaStream_t)stream,
 	                        nullptr, window, pos_origin, pos_count);
+}
+
+// Per-segment totals of the cumsum of 1/speed for segments [seg_begin, seg_end) of a curve: the part of
+// util/resampling.py:120-126 that a rank of a time-sharded job contributes (dist.TimeShard.positions
+// all-gathers the slices and hands the whole array to par_speed_to_pos_range_sums_f64).
+extern "C" PAR_API int par_segment_sums_f64(const double *sampletimes, const double *speeds, int64_t k,
+                                            int64_t seg_begin, int64_t seg_end, double *sums, unsigned flags,
+                                            int device, void *stream) {
+	if (!(flags & PAR_DEVICE_PTRS)) { set_error("segment_sums: device pointers only"); return PAR_EUNSUPPORTED; }
+	if (!sampletimes || !speeds || k < 2 || seg_begin < 0 || seg_end < seg_begin || seg_end > k - 1 || (!sums && seg_end > seg_begin)) {
+		set_error("segment_sums: bad argument");
+		return PAR_EINVAL;
+	}
+	int rc = use_device(device);
+	if (rc != PAR_OK) return rc;
+	const int64_t cnt = seg_end - seg_begin;
+	if (cnt == 0) return PAR_OK;
+	cudaStream_t st = (cudaStream_t)stream;
+	std::vector<int64_t> seg_n(k - 1);
+	if ((rc = par_speed_segments(sampletimes, speeds, k, seg_n.data(), nullptr)) != PAR_OK) return rc;
+	char *pin = g_pinned.get(((size_t)cnt * 2 + 1) * 8);
+	if (!pin) { set_error("segment_sums: pinned staging allocation failed"); return PAR_ECUDA; }
+	double *h_sp = (double *)pin;
+	int64_t *h_n = (int64_t *)(h_sp + cnt + 1);
+	memcpy(h_sp, speeds + seg_begin, (size_t)(cnt + 1) * 8);
+	memcpy(h_n, seg_n.data() + seg_begin, (size_t)cnt * 8);
+	DevBuf d_tab(st);
+	if ((rc = d_tab.alloc(((size_t)cnt * 2 + 1) * 8)) != PAR_OK) return rc;
+	PAR_CUDA(cudaMemcpyAsync(d_tab.p, pin, ((size_t)cnt * 2 + 1) * 8, cudaMemcpyHostToDevice, st));
+	if ((rc = launch_segment_sums(d_tab.as<double>(), (const int64_t *)(d_tab.as<double>() + cnt + 1), cnt, sums, st)) != PAR_OK)
+		return rc;
+	PAR_CUDA(cudaStreamSynchronize(st));
+	return PAR_OK;
+}
+
+extern "C" PAR_API int par_speed_to_pos_range_sums_f64(const double *sampletimes, const double *speeds, int64_t k,
+                                                       double num_input_samples, double lo_pos, double hi_pos,
+                                                       const double *seg_sums, double *pos, int64_t cap,
+                                                       int64_t *pos_origin, int64_t *pos_count, int64_t *m,
+                                                       unsigned flags, int device, void *stream) {
+	if (!(flags & PAR_DEVICE_PTRS)) { set_error("speed_to_pos_range: device pointers only"); return PAR_EUNSUPPORTED; }
+	if (!sampletimes || !speeds || k < 2 || !m || !pos_origin || !pos_count || !pos || !seg_sums || !(lo_pos <= hi_pos)) {
+		set_error("speed_to_pos_range: bad argument");
+		return PAR_EINVAL;
+	}
+	int rc = use_device(device);
+	if (rc != PAR_OK) return rc;
+	std::vector<int64_t> seg_n(k - 1);
+	int64_t total = 0;
+	if ((rc = par_speed_segments(sampletimes, speeds, k, seg_n.data(), &total)) != PAR_OK) return rc;
+	const double window[2] = {lo_pos, hi_pos};
+	return positions_device(sampletimes, speeds, k, num_input_samples, seg_n, total, pos, cap, m, (cudaStream_t)stream,
+	                        nullptr, window, pos_origin, pos_count, seg_sums);
 }
 
 // Resample with DEVICE positions; signal / out are host or device according to `flags`.

@@ -116,11 +116,24 @@ class TimeShard:
         _lib.check(rc, "par_stft_range_f32")
         return out
 
-    def positions(self, sampletimes, speeds, device, out=None):
+    def segment_slice(self, n_seg):
+        """Balanced block ``(per, a, b)`` of curve segments whose totals this rank computes."""
+        per = -(-n_seg // self.world)
+        a = min(self.rank * per, n_seg)
+        return per, a, min(a + per, n_seg)
+
+    def positions(self, sampletimes, speeds, device, out=None, group=None, share_sums=True):
         """This rank's slice of the read positions of a speed curve: the positions that fall into
-        ``[s0 - 1, s1 + 1]`` plus the segment after them (``par_speed_to_pos_range_f64``).
-        Returns ``(pos_slice, pos_origin, m_global)``; ``pos_slice[i]`` is position ``pos_origin + i``."""
+        ``[s0 - 1, s1 + 1]`` plus the segment after them.  Returns ``(pos_slice, pos_origin, m_global)``;
+        ``pos_slice[i]`` is position ``pos_origin + i``.
+
+        With several ranks (and ``share_sums``) the per-segment totals the serial offset chain needs are
+        computed once per JOB instead of once per rank: every rank sums its block of segments
+        (``par_segment_sums_f64``), one all-gather of ``8 * n_segments`` bytes shares them, and
+        ``par_speed_to_pos_range_sums_f64`` expands the rank's window.  Otherwise
+        ``par_speed_to_pos_range_f64`` does everything locally.  Both give identical bits."""
         import torch
+        import torch.distributed as dist
         L = _lib.lib()
         st = np.ascontiguousarray(sampletimes, dtype=np.float64)
         sp = np.ascontiguousarray(speeds, dtype=np.float64)
@@ -132,10 +145,25 @@ class TimeShard:
         lo = -np.inf if self.rank == 0 else float(self.s0) - 1.0
         hi = np.inf if self.rank == self.world - 1 else float(self.s1) + 1.0
         stream = torch.cuda.current_stream(out.device).cuda_stream
-        rc = L.par_speed_to_pos_range_f64(st.ctypes.data, sp.ctypes.data, len(st), float(self.n), lo, hi, out.data_ptr(),
-                                          out.numel(), box[0:].ctypes.data, box[1:].ctypes.data, box[2:].ctypes.data,
-                                          _lib.PAR_DEVICE_PTRS, out.device.index, stream)
-        _lib.check(rc, "par_speed_to_pos_range_f64")
+        if share_sums and self.world > 1 and dist.is_initialized():
+            n_seg = len(st) - 1
+            per, a, b = self.segment_slice(n_seg)
+            mine = torch.zeros(per, dtype=torch.float64, device=out.device)
+            rc = L.par_segment_sums_f64(st.ctypes.data, sp.ctypes.data, len(st), a, b, mine.data_ptr(), _lib.PAR_DEVICE_PTRS,
+                                        out.device.index, stream)
+            _lib.check(rc, "par_segment_sums_f64")
+            sums = torch.empty(per * self.world, dtype=torch.float64, device=out.device)
+            dist.all_gather_into_tensor(sums, mine, group=group)
+            rc = L.par_speed_to_pos_range_sums_f64(st.ctypes.data, sp.ctypes.data, len(st), float(self.n), lo, hi,
+                                                   sums.data_ptr(), out.data_ptr(), out.numel(), box[0:].ctypes.data,
+                                                   box[1:].ctypes.data, box[2:].ctypes.data, _lib.PAR_DEVICE_PTRS,
+                                                   out.device.index, stream)
+            _lib.check(rc, "par_speed_to_pos_range_sums_f64")
+        else:
+            rc = L.par_speed_to_pos_range_f64(st.ctypes.data, sp.ctypes.data, len(st), float(self.n), lo, hi, out.data_ptr(),
+                                              out.numel(), box[0:].ctypes.data, box[1:].ctypes.data, box[2:].ctypes.data,
+                                              _lib.PAR_DEVICE_PTRS, out.device.index, stream)
+            _lib.check(rc, "par_speed_to_pos_range_f64")
         return out[:int(box[1])], int(box[0]), int(box[2])
 
     def output_range(self, pos, pos_origin=0, m=None):

@@ -26,8 +26,10 @@ centre frequency [Hz], height [Hz], fraction of the width to average on either s
 
 
 def to_dB(a):
-    """util/units.py:27-28."""
-    return 20 * np.log10(a)
+    """util/units.py:27-28.  Evaluated in float64: the reference's CPU back-end hands its tools float64 magnitudes
+    (util/fourier.py:157 promotes), and a float32 decibel value near -100 dB would carry an error of several 1e-6 dB
+    that the gain curves of the dropout tools turn into the same RELATIVE error of the audio."""
+    return 20 * np.log10(np.asarray(a, dtype=np.float64))
 
 
 def to_fac(a):
@@ -161,12 +163,18 @@ def max_mono(signal, fft_size=512, hop=32):
 def heuristic_band_peaks(imdata_db, sr, fft_size, f_lower=100, f_upper=15000, num_bands=5):
     """The per-band valley detection of dropouts_gui.py:251, :269-288: integer band edges
     (``np.logspace(..., dtype=uint16)``), band bins by truncation, ``find_peaks(-vol, prominence=5)``.
-    Returns ``[(f_lo, f_hi, bin_lo, bin_hi, peaks)]`` from the top band down."""
+    Returns ``[(f_lo, f_hi, bin_lo, bin_hi, peaks)]`` from the top band down.
+
+    The reference multiplies the ``np.uint16`` band edge by ``fft_size`` directly.  Under numpy >= 2 (NEP 50) that
+    product wraps in uint16 and every band comes out empty (the tool then returns its input unchanged); under the
+    numpy 1.x the reference was written for it promotes to a Python-sized integer.  This follows the intended
+    arithmetic: the edge is converted to ``int`` first (``tests/golden/make_golden_dropouts_full.py`` records both
+    behaviours of the unmodified reference)."""
     bands = np.logspace(np.log2(f_lower), np.log2(f_upper), num=num_bands, endpoint=True, base=2, dtype=np.uint16)
     out = []
     for f_lo, f_hi in reversed(list(zip(bands[:-1], bands[1:]))):
-        bin_lo = int(f_lo * fft_size / sr)
-        bin_hi = int(f_hi * fft_size / sr)
+        bin_lo = int(int(f_lo) * fft_size / sr)
+        bin_hi = int(int(f_hi) * fft_size / sr)
         vol = np.mean(imdata_db[bin_lo:bin_hi], axis=0)
         peaks, _ = scipy.signal.find_peaks(-vol, prominence=5, rel_height=0.5)
         out.append((int(f_lo), int(f_hi), bin_lo, bin_hi, peaks))

@@ -1,2 +1,4 @@
 #!/bin/bash
-bash scripts/try_variants.sh "-DSINC_BLOCK_UNROLL=2" "-DSINC_BLOCK_UNROLL=2 -DSINC_EXPERIMENT_ALL_FC1" "-DSINC_BLOCK_UNROLL=2 -DSINC_EXPERIMENT_ALL_LOWPASS" "-DSINC_EXACT_MASK=1023" "-DSINC_EXACT_MASK=1023 -DSINC_EXPERIMENT_ALL_LOWPASS" "-DSINC_THREADS_N=512 -DSINC_MIN_BLOCKS=1" > gpurun_out/variants.log 2>&1; cat gpurun_out/variants.log
+python -m pytest tests -m gpu -q -x --timeout 1200 > gpurun_out/pytest_gpu.log 2>&1; tail -6 gpurun_out/pytest_gpu.log
+python bench.py --steps 10 > gpurun_out/bench_r2b.json 2> gpurun_out/bench_r2b.err; tail -c 3000 gpurun_out/bench_r2b.json; tail -5 gpurun_out/bench_r2b.err
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_r2b.json 2> gpurun_out/bench_ref_r2b.err; tail -c 900 gpurun_out/bench_ref_r2b.json

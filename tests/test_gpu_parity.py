@@ -577,6 +577,97 @@ def test_time_shards_reassemble_to_the_single_gpu_result(par, fourier, resamplin
     assert np.array_equal(np.concatenate(l_parts, axis=1).T, full_l)
 
 
+@pytest.mark.parametrize("workload,channels,points", [("cfg2", 2, 100000), ("cfg3", 1, 100000)])
+def test_parity_at_baseline_sizes_sampled(par, workload, channels, points):
+    """BASELINE configs[1] (600 s, 96 kHz) and configs[2] (3600 s, 192 kHz; positions up to 6.9e8, 675 k curve
+    segments) at FULL length: the read positions at 10^5 random outputs bit for bit against the serial float64
+    recurrence, the resampled values of those outputs against the float64 oracle on the same taps, and a set of STFT
+    frames -- bench.sampled_parity, the check bench.py also prints as `parity`."""
+    import torch
+    import bench
+    from pyaudiorestoration_b200 import _lib
+    L = _lib.lib()
+    dev = torch.device("cuda", _lib.device())
+    sr, dur, _, _ = bench.WORKLOADS[workload]
+    n = int(sr * dur)
+    x = torch.empty((channels, n), dtype=torch.float32, device=dev)
+    for c in range(channels):
+        bench.device_synth(torch, x[c], sr, 77 + c)
+    curve = bench.wow_curve(dur, sr)
+    st, sp = np.ascontiguousarray(curve[:, 0] * sr), np.ascontiguousarray(curve[:, 1])
+    cap = int(n * 1.02) + 4096
+    pos = torch.empty(cap, dtype=torch.float64, device=dev)
+    out = torch.empty((channels, cap), dtype=torch.float32, device=dev)
+    T, F = int(L.par_stft_num_frames(n, bench.N_FFT, bench.HOP)), bench.N_FFT // 2 + 1
+    S = torch.empty((channels, T, F), dtype=torch.complex64, device=dev)
+    win = bench.get_window()
+    m_box = np.zeros(1, np.int64)
+    _lib.check(L.par_stft_f32(x.data_ptr(), n, 1, channels, n, bench.N_FFT, bench.HOP, 1, win.ctypes.data, S.data_ptr(), F, T * F,
+                              _lib.PAR_DEVICE_PTRS, dev.index, None), "stft")
+    _lib.check(L.par_speed_to_pos_f64(st.ctypes.data, sp.ctypes.data, len(st), float(n), pos.data_ptr(), cap, m_box.ctypes.data,
+                                      _lib.PAR_DEVICE_PTRS, dev.index, None), "positions")
+    m = int(m_box[0])
+    _lib.check(L.par_sinc_resample_f32(pos.data_ptr(), m, x.data_ptr(), n, 1, channels, n, bench.NT, out.data_ptr(), 1, cap,
+                                       _lib.PAR_DEVICE_PTRS, dev.index, None), "sinc")
+    torch.cuda.synchronize(dev)
+    res = bench.sampled_parity(torch, x, pos, m, out, S, curve, sr, n, n_points=points, n_frames=32, seed=5)
+    del x, pos, out, S
+    torch.cuda.empty_cache()
+    L.par_release_cached_memory(dev.index)
+    assert res["output_count_equal"] and res["positions_bit_exact"], res
+    assert res["sinc_points"] >= 0.9 * points * channels
+    assert res["sinc_rel_l2"] <= TOL and res["sinc_rel_max"] <= TOL, res
+    assert res["stft_rel_l2"] <= TOL, res
+
+
+def test_shared_segment_sums_give_the_same_position_slices(par, resampling):
+    """Time-sharded positions with the per-segment totals computed in slices and shared (what
+    dist.TimeShard.positions does over an all-gather) equal the all-local range call and the global array,
+    bit for bit -- also when the curve runs past the end of the signal and the chunks are shorter than a
+    curve segment (the windowed search must not walk into the segments behind the end)."""
+    import torch
+    from pyaudiorestoration_b200 import _lib
+    L = _lib.lib()
+    dev = torch.device("cuda", _lib.device())
+    for sr, dur, hop, n_in, world in ((48000, 6.0, 1024, 48000 * 6, 3), (44100, 4.0, 4096, int(44100 * 2.5), 7)):
+        curve = wow_curve(dur, sr, hop, depth=0.05)
+        st = np.ascontiguousarray(curve[:, 0] * sr)
+        sp = np.ascontiguousarray(curve[:, 1])
+        full = resampling.speed_to_pos(st, sp, n_in)
+        k, n_seg = len(st), len(st) - 1
+        per = -(-n_seg // world)
+        sums = torch.zeros(per * world, dtype=torch.float64, device=dev)
+        for r in range(world):
+            a, b = min(r * per, n_seg), min(r * per + per, n_seg)
+            _lib.check(L.par_segment_sums_f64(st.ctypes.data, sp.ctypes.data, k, a, b, sums[r * per:].data_ptr(),
+                                              _lib.PAR_DEVICE_PTRS, dev.index, None), "par_segment_sums_f64")
+        bounds = np.linspace(0, n_in, world + 1)
+        for r in range(world):
+            lo = -np.inf if r == 0 else bounds[r] - 1.0
+            hi = np.inf if r == world - 1 else bounds[r + 1] + 1.0
+            got = []
+            for shared in (True, False):
+                out = torch.full((len(full) + 16,), np.nan, dtype=torch.float64, device=dev)
+                box = np.zeros(3, dtype=np.int64)
+                if shared:
+                    rc = L.par_speed_to_pos_range_sums_f64(st.ctypes.data, sp.ctypes.data, k, float(n_in), lo, hi, sums.data_ptr(),
+                                                           out.data_ptr(), out.numel(), box[0:].ctypes.data, box[1:].ctypes.data,
+                                                           box[2:].ctypes.data, _lib.PAR_DEVICE_PTRS, dev.index, None)
+                else:
+                    rc = L.par_speed_to_pos_range_f64(st.ctypes.data, sp.ctypes.data, k, float(n_in), lo, hi, out.data_ptr(),
+                                                      out.numel(), box[0:].ctypes.data, box[1:].ctypes.data, box[2:].ctypes.data,
+                                                      _lib.PAR_DEVICE_PTRS, dev.index, None)
+                _lib.check(rc, "positions range")
+                o0, cnt, m = (int(v) for v in box)
+                assert m == len(full) and cnt > 0
+                got.append((o0, out[:cnt].cpu().numpy()))
+                assert np.array_equal(got[-1][1], full[o0:o0 + cnt])
+                # the slice covers every position inside the window
+                inside = np.nonzero((full >= lo) & (full <= hi))[0]
+                assert len(inside) == 0 or (o0 <= inside[0] and inside[-1] < o0 + cnt)
+            assert got[0][0] == got[1][0] and np.array_equal(got[0][1], got[1][1])
+
+
 def test_range_entry_points_reject_uncovered_slices(par):
     import torch
     from pyaudiorestoration_b200 import _lib
@@ -637,8 +728,9 @@ def test_cfg4_dropout_heal_and_locate(golden_dir, fourier):
     assert len(got) == len(want_h) == 4
     for g, w in zip(got, want_h):
         assert np.array_equal(g[4], w)
+    assert any(len(g[4]) for g in got)                           # band edges no longer overflow: valleys are found
     out = dropouts.heuristic(x[:40000, None], sr, fft_size, hop)
-    assert out.shape == (40000, 1) and np.isfinite(out).all()
+    assert out.shape == (40000, 1) and np.isfinite(out).all() and np.any(out[:, 0] != x[:40000])
 
 
 def test_cfg4_max_mono(fourier):
@@ -649,6 +741,51 @@ def test_cfg4_max_mono(fourier):
     for k in ("max", "min"):
         # a cell flips channel only if |L| and |R| agree to float32 rounding; allow a handful of such cells
         assert rel_l2(got[k].astype(np.float64), want[k].astype(np.float64)) <= 5e-6
+
+
+def test_cfg4_full_file_against_the_reference_run(golden_dir, fourier):
+    """BASELINE config 4 on the WHOLE samples/dropouts_sample.flac against outputs of the UNMODIFIED reference
+    (tests/golden/make_golden_dropouts_full.py): heal with all 32 markers, the Alt-drag locator's integer frame
+    indices (bit-exact) and markers, max/min-mono, and the heuristic batch tool's per-band peaks and output."""
+    from pyaudiorestoration_b200 import dropouts
+    z = _load(golden_dir, "dropouts_full")
+    x = (z["pcm"].astype(np.float64) / 32768.0).astype(np.float32)
+    sr, fft_size, hop = int(z["sr"]), int(z["fft_size"]), int(z["hop"])
+    # D1
+    drops = [dropouts.Dropout(*m) for m in z["markers"].tolist()]
+    assert len(drops) == 32
+    regs = [dropouts.marker_region(d, sr, fft_size, hop) for d in drops]
+    assert np.array_equal(np.array(regs, dtype=np.int64), z["regions"])
+    y = dropouts.heal(x[:, None], sr, drops, fft_size, hop, channels=[0])[:, 0]
+    assert y.dtype == np.float32 and y.shape == z["healed"].shape
+    assert rel_max(y, z["healed"]) <= TOL and rel_l2(y.astype(np.float64), z["healed"].astype(np.float64)) <= TOL
+    # D2: GPU magnitudes in, the reference's own peak indices out
+    (t0, f0), (t1, f1) = z["loc_corners"]
+    f_lo, f_hi = max(min(f0, f1), 1), min(max(f0, f1), sr // 2 - 1)
+    mag = fourier.get_mag(x, fft_size, hop, "blackmanharris", 1)
+    peaks, found = dropouts.locate(mag, sr, fft_size, hop, min(t0, t1), max(t0, t1), f_lo, f_hi,
+                                   sensitivity=float(z["loc_sensitivity"]), width_ms=float(z["loc_width_ms"]))
+    assert peaks.dtype.kind == "i" and np.array_equal(peaks, z["loc_peaks"])
+    got = np.array([(m.t - m.width / 2, m.f - m.height / 2, m.t + m.width / 2, m.f + m.height / 2) for m in found])
+    assert got.shape == z["loc_markers"].shape and np.allclose(got, z["loc_markers"], rtol=0, atol=1e-9)
+    # D3a
+    d = int(z["mm_right_delay"])
+    pcm_r = np.zeros_like(z["pcm"])
+    pcm_r[d:] = (z["pcm"][:-d].astype(np.int32) * 4 // 5).astype(np.int16)
+    right = (pcm_r.astype(np.float64) / 32768.0).astype(np.float32)
+    mm = dropouts.max_mono(np.stack([x, right], axis=1), fft_size, hop)
+    for k, ref in (("max", z["mm_max"]), ("min", z["mm_min"])):
+        # a cell flips channel only where |L| and |R| agree to float32 rounding; allow a handful of such cells
+        assert rel_l2(mm[k].astype(np.float64), ref.astype(np.float64)) <= 5e-6
+    # D3b: per-band valley indices (bit-exact) and the corrected signal
+    mag_h = fourier.get_mag(x, fft_size, hop, "hann")
+    bands = dropouts.heuristic_band_peaks(dropouts.to_dB(np.array(mag_h)), sr, fft_size, 100, 15000, 5)
+    assert len(bands) == 4
+    for i, b in enumerate(bands):
+        assert len(b[4]) > 0 and np.array_equal(b[4], z[f"heur_band_peaks_{i}"])
+    out = dropouts.heuristic(x[:, None], sr, fft_size, hop)[:, 0]
+    assert np.sum(out != x) > 1000                                  # the tool really changed the signal
+    assert rel_l2(out.astype(np.float64), z["heur_out"].astype(np.float64)) <= TOL and rel_max(out, z["heur_out"]) <= 2 * TOL
 
 
 # ----------------------------------------------------------------------------------------- trackers (8f rank 1)

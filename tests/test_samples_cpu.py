@@ -91,3 +91,53 @@ def test_tracker_oracle_matches_reference_classes_bitwise(golden_dir):
     for mode in ("peak", "peak_track", "cog"):
         times, freqs = onp.track_ref(mode, spec, trail, fft_size, hop, sr)
         assert np.array_equal(times, z[mode + "__times"]) and np.array_equal(freqs, z[mode + "__freqs"]), mode
+
+
+# ---- BASELINE config 4 on the WHOLE sample: fixtures from tests/golden/make_golden_dropouts_full.py --------------
+@pytest.fixture(scope="module")
+def full(golden_dir):
+    z = np.load(os.path.join(golden_dir, "dropouts_full.npz"))
+    x = (z["pcm"].astype(np.float64) / 32768.0).astype(np.float32)
+    return z, x, int(z["sr"]), int(z["fft_size"]), int(z["hop"])
+
+
+def test_cfg4_full_oracle_heal_all_markers_bitwise(full):
+    """D1: the oracle's heal equals the unmodified Canvas.resample_files on the whole file, all 32 markers."""
+    z, x, sr, fft_size, hop = full
+    assert len(z["markers"]) == 32
+    assert np.array_equal(onp.heal_regions(z["markers"], sr, fft_size, hop), z["regions"])
+    y = onp.heal_ref(x, sr, z["markers"], fft_size, hop)
+    assert y.dtype == np.float32 and np.array_equal(y, z["healed"])
+
+
+def test_cfg4_full_oracle_locator_peaks_are_the_references(full):
+    """D2: the integer frame indices find_peaks returned INSIDE the reference's Alt-drag handler
+    (dropout_healer_gui.py:185-204) equal the oracle's, so the oracle is pinned for the bit-exact index check."""
+    z, x, sr, fft_size, hop = full
+    (t0, f0), (t1, f1) = z["loc_corners"]
+    f_lo, f_hi = max(min(f0, f1), 1), min(max(f0, f1), sr // 2 - 1)            # Spectrum.get_times_freqs, util/spectrum.py:173-178
+    mag = onp.to_mag(onp.stft_ref(x, fft_size, hop))
+    peaks = onp.locate_peaks_ref(mag, sr, fft_size, hop, min(t0, t1), max(t0, t1), f_lo, f_hi, float(z["loc_sensitivity"]))
+    assert len(z["loc_peaks"]) >= 30 and np.array_equal(peaks, z["loc_peaks"])
+
+
+def test_cfg4_full_oracle_batch_tool(full):
+    """D3: max/min-mono outputs and the per-band peaks of process_heuristic (dropouts_gui.py:137-163, :241-323)."""
+    z, x, sr, fft_size, hop = full
+    right = np.zeros_like(x)
+    d = int(z["mm_right_delay"])
+    pcm_r = np.zeros_like(z["pcm"])
+    pcm_r[d:] = (z["pcm"][:-d].astype(np.int32) * 4 // 5).astype(np.int16)
+    right = (pcm_r.astype(np.float64) / 32768.0).astype(np.float32)
+    out = onp.max_mono_ref(np.stack([x, right], axis=1), fft_size, hop)
+    # the numpy back-end hands istft a complex128 matrix, so the reference's result is float64; the fixture keeps float32
+    assert np.array_equal(out["max"].astype(np.float32), z["mm_max"]) and np.array_equal(out["min"].astype(np.float32), z["mm_min"])
+    # heuristic: under this numpy the unmodified reference finds nothing (uint16 overflow) ...
+    assert bool(z["heur_np2_unchanged"]) and not z["heur_np2_band_peak_counts"].any()
+    # ... with integer band edges (numpy 1.x arithmetic) it finds these valleys, and so does the oracle
+    cpu_h = onp.to_mag(onp.stft_ref(x, fft_size, hop, "hann"))
+    got = onp.heuristic_peaks_ref(cpu_h, sr, fft_size, 100, 15000, 5)
+    assert len(got) == 4
+    for i, g in enumerate(got):
+        assert len(g) > 0 and np.array_equal(g, z[f"heur_band_peaks_{i}"])
+    assert np.sum(z["heur_out"] != x) > 1000
