@@ -293,8 +293,10 @@ struct AudioUploader {
 	int64_t n = 0, stride = 1, ch_stride = 0, n_al = 4, span = 0, done = 0;
 	int n_ch = 1;
 	bool interleaved = false;
-	DevBuf raw;
-	explicit AudioUploader(cudaStream_t st) : raw(st) {}
+	int device = 0;
+	DevBuf raw, stage;
+	static constexpr int64_t STAGE_FLOATS = 8ll << 20;     // 32 MB of staging for widely strided channels
+	explicit AudioUploader(cudaStream_t st) : raw(st), stage(st) {}
 
 	int init(const float *src_, int64_t n_, int64_t stride_, int n_ch_, int64_t ch_stride_) {
 		src = src_; n = n_; stride = stride_; n_ch = n_ch_; ch_stride = ch_stride_;
@@ -302,6 +304,14 @@ struct AudioUploader {
 		span = n > 0 ? (n - 1) * stride + (int64_t)(n_ch - 1) * ch_stride + 1 : 0;
 		interleaved = n > 0 && stride > 1 && (n_ch == 1 || (ch_stride > 0 && ch_stride < stride)) &&
 		              span <= 4 * n * (int64_t)n_ch + 64;
+		cudaGetDevice(&device);
+		// a channel view with a wider stride (one column of an array with more than 4 channels): the strided
+		// span goes up in bounded pieces and is de-interleaved on the device -- a 2-D copy with 4-byte rows
+		// would issue one DMA descriptor per sample
+		if (!interleaved && stride > 1) {
+			int rc = stage.alloc((size_t)STAGE_FLOATS * sizeof(float));
+			if (rc != PAR_OK) return rc;
+		}
 		return raw.alloc((size_t)((interleaved ? span + 4 : n_al * n_ch) + 4) * sizeof(float));
 	}
 	DevAudio view() const {
@@ -326,9 +336,14 @@ struct AudioUploader {
 					PAR_CUDA(cudaMemcpyAsync(d + c * n_al + done, src + c * ch_stride + done,
 					                         (size_t)(hi - done) * sizeof(float), cudaMemcpyHostToDevice, up));
 				} else {
-					PAR_CUDA(cudaMemcpy2DAsync(d + c * n_al + done, sizeof(float), src + c * ch_stride + done * stride,
-					                           stride * sizeof(float), sizeof(float), hi - done,
-					                           cudaMemcpyHostToDevice, up));
+					const int64_t piece = STAGE_FLOATS / stride > 0 ? STAGE_FLOATS / stride : 1;
+					for (int64_t a0 = done; a0 < hi; a0 += piece) {
+						const int64_t cnt = hi - a0 < piece ? hi - a0 : piece;
+						PAR_CUDA(cudaMemcpyAsync(stage.p, src + c * ch_stride + a0 * stride,
+						                         (size_t)((cnt - 1) * stride + 1) * sizeof(float), cudaMemcpyHostToDevice, up));
+						int rc = launch_deinterleave(stage.as<float>(), cnt, stride, 1, 0, d + c * n_al + a0, n_al, device, up);
+						if (rc != PAR_OK) return rc;
+					}
 				}
 			}
 		}

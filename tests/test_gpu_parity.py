@@ -107,6 +107,21 @@ def test_stft_strided_column_view(golden_dir, fourier):
     _check_stft(s, np.ascontiguousarray(inter[:, 1]), 1024, 256, "blackmanharris", 1)
 
 
+def test_column_of_a_wide_interleaved_array(fourier, resampling, monkeypatch):
+    """signal[:, c] of an 8-channel (frames, channels) array, as the GUIs pass it: the strided span goes up in
+    staged pieces and is de-interleaved on the device (no per-sample DMA rows); several pipeline chunks."""
+    monkeypatch.setenv("PAR_B200_CHUNK_BYTES", str(1 << 18))
+    sig = np.stack([synth(60000, 300 + c) for c in range(8)], axis=1)
+    assert sig.strides == (32, 4)
+    for c in (0, 5):
+        s = fourier.stft(sig[:, c], 1024, 256)
+        _check_stft(s, np.ascontiguousarray(sig[:, c]), 1024, 256, "blackmanharris", 1)
+    pos = np.linspace(300.0, 59000.0, 40000)
+    y = resampling.sinc_wrapper(pos, sig[:, 3], 0, 50)
+    ref = oracle.sinc_c(pos, np.ascontiguousarray(sig[:, 3]), 50)
+    assert rel_l2(y.astype(np.float64), ref.astype(np.float64)) <= TOL and rel_max(y, ref) <= TOL
+
+
 @pytest.mark.parametrize("n_fft,hop", [(32, 8), (64, 16), (128, 32), (256, 64), (512, 32), (1024, 256),
                                        (2048, 512), (4096, 1024), (8192, 2048), (16384, 4096),
                                        (32768, 8192), (4096, 1000), (4096, 4096), (1024, 3000)])
