@@ -109,6 +109,31 @@ PAR_API int par_istft_f32(const void *S, int n_fft, int64_t n_frames, int64_t s_
                   int64_t length, float *y, int64_t y_stride, int64_t y_ch_stride,
                   unsigned flags, int device, void *stream);
 
+/* ---- stft -> STFT-domain mask -> istft, the spectrogram never leaving the device --------------------------------
+ * The bodies the reference's tools run between util.fourier.stft and util.fourier.istft on a signal padded by
+ * fix_length(signal, n + n_fft // 2) (dropout_healer_gui.py:129-164, dropouts_gui.py:148-159,
+ * renoiser_gui.py:310-317):  y = istft(op(stft(pad(x))), length = n, hop_length = hop), one upload and one
+ * download per call.  window / syn_window: HOST float32[n_fft] (analysis / synthesis; the tools use
+ * blackmanharris for both).  n_fft: a power of two in [32, 32768].  Operators:
+ *   PAR_SPEC_GATE         renoiser_gui.py:273-278   params = float64 profile_db[n_fft/2+1], n_params = n_fft/2+1:
+ *                         S[f, t] *= 10^(gain_db/20) wherever 20 log10(|S| + 1e-7) <= profile_db[f]; n_ch outputs
+ *   PAR_SPEC_SELECT_MAX / _MIN / _BOTH   dropouts_gui.py:153-161   n_ch must be 2: per cell the louder (quieter)
+ *                         of the two channels; 1 output channel (BOTH: 2 -- max, then min)
+ *   PAR_SPEC_HEAL         dropout_healer_gui.py:134-162   params = int64 regions[n_params][5] = (frame_b, frame_a,
+ *                         frame_surrounding, bin_l, bin_u) per marker (:136-141), applied in order: mean dB level of the
+ *                         surrounding frames before / after the gap, bilinear blend across it, boost clipped to
+ *                         [earlier boost, 255] dB; n_ch outputs
+ * y: n samples per output channel (channel c at + c * y_ch_stride, element stride y_stride). */
+#define PAR_SPEC_GATE 0
+#define PAR_SPEC_SELECT_MAX 1
+#define PAR_SPEC_SELECT_MIN 2
+#define PAR_SPEC_SELECT_BOTH 3
+#define PAR_SPEC_HEAL 4
+PAR_API int par_spectral_process_f32(const float *x, int64_t n, int64_t x_stride, int n_ch, int64_t x_ch_stride,
+                             int n_fft, int hop, const float *window, const float *syn_window, int op,
+                             const void *params, int64_t n_params, double gain_db, float *y, int64_t y_stride,
+                             int64_t y_ch_stride, unsigned flags, int device, void *stream);
+
 /* ---- positions: util/resampling.py:93-137 speed_to_pos --------------------------------------
  * Host-only, serial, bit-exact: the error-diffused integer segment lengths (:111-118).
  * seg_n: int64[k-1].  Returns sum(seg_n) in *total. */

@@ -22,7 +22,7 @@ from scipy import signal as dsp
 __all__ = [
     "get_window_f32", "reflect_pad", "stft_ref", "stft_f64", "to_mag", "istft_ref",
     "window_sumsquare", "fix_length", "speed_to_pos", "speed_segments",
-    "sinc_resample", "hanning_f32", "linear_resample", "lag_to_positions",
+    "sinc_resample", "hanning_f32", "linear_resample", "lag_to_positions", "noise_gate_ref",
 ]
 
 
@@ -351,6 +351,18 @@ def max_mono_ref(signal, fft_size, hop):
     for name, mask in (("max", np.abs(d_l) > np.abs(d_r)), ("min", np.abs(d_l) < np.abs(d_r))):
         out[name] = istft_ref(np.where(mask, d_l, d_r), hop_length=hop, length=n)
     return out
+
+
+def noise_gate_ref(signal, profile_db, gain_db, fft_size, hop):
+    """renoiser_gui.py:273-278 (get_mask_fac) + :303-319 (run_resample) for one channel: pad, STFT, scale every cell whose
+    ``to_dB(to_mag(S))`` does not exceed the profile by ``to_fac(gain)`` (as float32), iSTFT."""
+    x = np.asarray(signal)
+    n = len(x)
+    pad = fix_length(x, n + fft_size // 2, axis=0)
+    spec = np.array(stft_ref(pad, fft_size, hop))
+    gain_mask = np.where(20 * np.log10(np.array(to_mag(spec))) > np.expand_dims(np.asarray(profile_db), axis=1), 0.0, gain_db)
+    fac = np.power(10, gain_mask / 20).astype(np.float32)
+    return istft_ref(spec * fac, hop_length=hop, length=n)
 
 
 def heuristic_peaks_ref(magnitude, sr, fft_size, f_lower, f_upper, num_bands):

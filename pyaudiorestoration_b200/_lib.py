@@ -20,12 +20,13 @@ PAR_ECAPACITY = -4
 PAR_MODE_LINEAR = 0
 PAR_MODE_SINC = 1
 PAR_TRACE_PEAK, PAR_TRACE_PEAK_TRACK, PAR_TRACE_COG = 0, 1, 2
+PAR_SPEC_GATE, PAR_SPEC_SELECT_MAX, PAR_SPEC_SELECT_MIN, PAR_SPEC_SELECT_BOTH, PAR_SPEC_HEAL = 0, 1, 2, 3, 4
 
 EXPORTS = (
     "par_last_error", "par_version", "par_device_count", "par_kernel_launch_count",
     "par_last_kernel_ms", "par_selftest_positions_quotient", "par_release_cached_memory", "par_host_alloc", "par_host_free", "par_stft_num_frames", "par_stft_f32",
     "par_istft_f32", "par_speed_segments", "par_speed_to_pos_f64", "par_sinc_resample_f32",
-    "par_linear_resample_f32", "par_varispeed_f32", "par_stft_range_f32", "par_resample_range_f32", "par_speed_to_pos_range_f64", "par_segment_sums_f64", "par_speed_to_pos_range_sums_f64", "par_trace_f32", "par_stft_trace_f32",
+    "par_linear_resample_f32", "par_varispeed_f32", "par_stft_range_f32", "par_resample_range_f32", "par_speed_to_pos_range_f64", "par_segment_sums_f64", "par_speed_to_pos_range_sums_f64", "par_spectral_process_f32", "par_trace_f32", "par_stft_trace_f32",
 )
 
 
@@ -77,6 +78,8 @@ def _declare(L):
                                          i64, u32, i32, vp]
     L.par_speed_to_pos_range_f64.restype = i32
     L.par_speed_to_pos_range_f64.argtypes = [vp, vp, i64, dbl, dbl, dbl, vp, i64, vp, vp, vp, u32, i32, vp]
+    L.par_spectral_process_f32.restype = i32
+    L.par_spectral_process_f32.argtypes = [vp, i64, i64, i32, i64, i32, i32, vp, vp, i32, vp, i64, dbl, vp, i64, i64, u32, i32, vp]
     L.par_segment_sums_f64.restype = i32
     L.par_segment_sums_f64.argtypes = [vp, vp, i64, i64, i64, vp, u32, i32, vp]
     L.par_speed_to_pos_range_sums_f64.restype = i32

@@ -596,6 +596,108 @@ PAR_API int par_istft_f32(const void *S, int n_fft, int64_t n_frames, int64_t s_
 	return PAR_OK;
 }
 
+// ---- stft -> mask -> istft with the spectrogram resident on the device -------------------
+PAR_API int par_spectral_process_f32(const float *x, int64_t n, int64_t x_stride, int n_ch, int64_t x_ch_stride,
+                             int n_fft, int hop, const float *window, const float *syn_window, int op,
+                             const void *params, int64_t n_params, double gain_db, float *y, int64_t y_stride,
+                             int64_t y_ch_stride, unsigned flags, int device, void *stream) {
+	if (!x || !y || !window || !syn_window) { set_error("spectral_process: null pointer"); return PAR_EINVAL; }
+	if (n < 1 || n_ch < 1 || n_fft < 32 || (n_fft & (n_fft - 1)) || n_fft > 32768 || hop < 1 || x_stride < 1 || y_stride < 1) {
+		set_error("spectral_process: bad size argument (n_fft: a power of two in [32, 32768])");
+		return PAR_EINVAL;
+	}
+	const bool select = op == PAR_SPEC_SELECT_MAX || op == PAR_SPEC_SELECT_MIN || op == PAR_SPEC_SELECT_BOTH;
+	if (!(op == PAR_SPEC_GATE || op == PAR_SPEC_HEAL || select) || (select && n_ch != 2) ||
+	    ((op == PAR_SPEC_GATE || (op == PAR_SPEC_HEAL && n_params > 0)) && !params) || n_params < 0) {
+		set_error("spectral_process: bad operator arguments");
+		return PAR_EINVAL;
+	}
+	int rc = use_device(device);
+	if (rc != PAR_OK) return rc;
+	cudaStream_t st = (cudaStream_t)stream;
+	const int64_t F = n_fft / 2 + 1;
+	const int64_t n_pad = n + n_fft / 2;                      // fix_length(signal, n + n_fft // 2), util/fourier.py:440-478
+	const int64_t n_pad_al = (n_pad + 3) & ~(int64_t)3;
+	const int64_t T = par_stft_num_frames(n_pad, n_fft, hop);
+	const int n_out = op == PAR_SPEC_SELECT_BOTH ? 2 : (select ? 1 : n_ch);
+	if (op == PAR_SPEC_GATE && n_params != F) { set_error("spectral_process: the gate needs one threshold per bin"); return PAR_EINVAL; }
+	int64_t g0 = 0, g1 = 0;
+	if (op == PAR_SPEC_HEAL) {
+		const int64_t *rg = (const int64_t *)params;
+		g0 = T;
+		for (int64_t r = 0; r < n_params; r++) {
+			const int64_t fb = rg[5 * r], fa = rg[5 * r + 1], ar = rg[5 * r + 2], bl = rg[5 * r + 3], bu = rg[5 * r + 4];
+			if (fb < 0 || fa <= fb || fa > T || ar < 1 || bl < 0 || bu - bl < 2 || bu > F) {
+				set_error("spectral_process: heal region outside the spectrogram (or thinner than 2 bins / 1 frame)");
+				return PAR_EINVAL;
+			}
+			if (fb < g0) g0 = fb;
+			if (fa > g1) g1 = fa;
+		}
+	}
+	const float *dwin = device_window(device, window, n_fft, st);
+	const float *dsyn = device_window(device, syn_window, n_fft, st);
+	if (!dwin || !dsyn) return PAR_ECUDA;
+
+	// ---- padded planar input on the device
+	DevBuf dx(st), dS(st), dframes(st), dy(st), dscratch(st);
+	AudioUploader up(st);
+	if ((rc = dx.alloc((size_t)n_ch * n_pad_al * sizeof(float))) != PAR_OK) return rc;
+	PAR_CUDA(cudaMemsetAsync(dx.p, 0, (size_t)n_ch * n_pad_al * sizeof(float), st));
+	if (flags & PAR_DEVICE_PTRS) {
+		if ((rc = launch_deinterleave(x, n, x_stride, n_ch, x_ch_stride, dx.as<float>(), n_pad_al, device, st)) != PAR_OK) return rc;
+	} else {
+		if ((rc = up.init(x, n, x_stride, n_ch, x_ch_stride)) != PAR_OK) return rc;
+		if ((rc = up.upload_to(n, st)) != PAR_OK) return rc;
+		const DevAudio da = up.view();
+		if ((rc = launch_deinterleave(da.p, n, da.stride, n_ch, da.ch_stride, dx.as<float>(), n_pad_al, device, st)) != PAR_OK) return rc;
+	}
+	// ---- analysis
+	if ((rc = dS.alloc((size_t)n_ch * T * F * sizeof(float2))) != PAR_OK) return rc;
+	StftArgs sa;
+	sa.x = dx.as<float>(); sa.n = n_pad; sa.x_stride = 1; sa.x_ch_stride = n_pad_al; sa.x_origin = 0;
+	sa.n_ch = n_ch; sa.n_fft = n_fft; sa.hop = hop; sa.zeropad = 1; sa.n_frames = T; sa.frame0 = 0;
+	sa.window = dwin; sa.out = dS.p; sa.out_pitch = F; sa.out_ch_stride = T * F; sa.magnitude = 0;
+	if ((rc = launch_stft(sa, device, st)) != PAR_OK) return rc;
+	// ---- mask
+	float2 *S = dS.as<float2>();
+	if (op == PAR_SPEC_GATE) {
+		if ((rc = dscratch.alloc((size_t)F * sizeof(double))) != PAR_OK) return rc;
+		PAR_CUDA(cudaMemcpyAsync(dscratch.p, params, (size_t)F * sizeof(double), cudaMemcpyHostToDevice, st));
+		PAR_CUDA(cudaStreamSynchronize(st));            // `params` is the caller's (possibly pageable) memory
+		if ((rc = launch_spec_gate(S, (int64_t)n_ch * T * F, (int)F, dscratch.as<double>(), gain_db, device, st)) != PAR_OK) return rc;
+	} else if (select) {
+		float2 *L = S, *R = S + T * F;
+		rc = launch_spec_select(L, R, T * F, op == PAR_SPEC_SELECT_MIN ? nullptr : L,
+		                        op == PAR_SPEC_SELECT_MIN ? L : (op == PAR_SPEC_SELECT_BOTH ? R : nullptr), device, st);
+		if (rc != PAR_OK) return rc;
+	} else if (n_params > 0) {
+		if ((rc = dscratch.alloc((size_t)(2 * F + (g1 - g0) * F) * sizeof(double))) != PAR_OK) return rc;
+		for (int c = 0; c < n_ch; c++)
+			if ((rc = launch_spec_heal(S + (int64_t)c * T * F, F, T, (int)F, (const int64_t *)params, n_params, g0, g1,
+			                           dscratch.as<double>(), device, st)) != PAR_OK)
+				return rc;
+	}
+	// ---- synthesis: istft(S, length=n, hop_length=hop), util/fourier.py:373-381 frame count
+	int64_t n_frames = (n + n_fft + hop - 1) / hop;
+	if (n_frames > T) n_frames = T;
+	if ((rc = dframes.alloc((size_t)n_out * n_frames * n_fft * sizeof(float))) != PAR_OK) return rc;
+	IstftArgs ia;
+	ia.S = S; ia.n_fft = n_fft; ia.n_frames = n_frames; ia.s_pitch = F; ia.s_ch_stride = T * F; ia.n_ch = n_out; ia.hop = hop;
+	ia.window = dsyn; ia.start = n_fft / 2; ia.length = n; ia.frames = dframes.as<float>();
+	if (flags & PAR_DEVICE_PTRS) {
+		ia.y = y; ia.y_stride = y_stride; ia.y_ch_stride = y_ch_stride;
+		return launch_istft(ia, device, st);
+	}
+	DevOut dyo;
+	if ((rc = alloc_out(dy, n, y_stride, n_out, y_ch_stride, st, &dyo)) != PAR_OK) return rc;
+	ia.y = dyo.p; ia.y_stride = dyo.stride; ia.y_ch_stride = dyo.ch_stride;
+	if ((rc = launch_istft(ia, device, st)) != PAR_OK) return rc;
+	if ((rc = download_out(dyo, y, 0, n, y_stride, n_out, y_ch_stride, st)) != PAR_OK) return rc;
+	PAR_CUDA(cudaStreamSynchronize(st));
+	return PAR_OK;
+}
+
 PAR_API int par_speed_segments(const double *sampletimes, const double *speeds, int64_t k,
                        int64_t *seg_n, int64_t *total) {
 	if (!sampletimes || !speeds || k < 2 || !seg_n) { set_error("speed_segments: bad argument"); return PAR_EINVAL; }

@@ -63,6 +63,13 @@ struct IstftArgs {
 };
 int launch_istft(const IstftArgs &a, int device, cudaStream_t st);
 
+// STFT-domain mask operators (spectral.cu); S is a device spectrogram, frames `pitch` float2 apart, bins contiguous
+int launch_spec_gate(float2 *S, int64_t cells, int F, const double *thr_db_dev, double gain_db, int device, cudaStream_t st);
+int launch_spec_select(const float2 *L, const float2 *R, int64_t cells, float2 *out_max, float2 *out_min, int device,
+                       cudaStream_t st);
+int launch_spec_heal(float2 *S, int64_t pitch, int64_t T, int F, const int64_t *regions, int64_t n_regions, int64_t g0,
+                     int64_t g1, double *scratch_dev, int device, cudaStream_t st);
+
 int launch_quotient_selftest(int64_t max_n, unsigned long long *mismatches_dev, cudaStream_t st);
 int launch_segment_sums(const double *speeds_dev, const int64_t *seg_n_dev, int64_t n_seg,
                         double *sums_dev, cudaStream_t st);

@@ -9,6 +9,7 @@ integer regions and peak indices as the reference:
 * ``marker_region`` <- dropout_healer_gui.py:99-109, :136-141  (time_2_frame / freq_2_bin rules)
 * ``locate``        <- dropout_healer_gui.py:185-242  (Alt-drag batch detection)
 * ``max_mono``      <- dropouts_gui.py:137-163        (process_max_mono)
+* ``noise_gate``    <- renoiser_gui.py:273-278, :303-319  (get_mask_fac / run_resample)
 * ``heuristic``     <- dropouts_gui.py:241-323        (process_heuristic)
 """
 import logging
@@ -83,18 +84,40 @@ def heal_gain_db(spectrum_db, drops, sr, fft_size, hop):
     return gain
 
 
-def heal(signal, sr, drops, fft_size=512, hop=32, channels=None):
+def _device_regions(drops, sr, fft_size, hop, n):
+    """The markers' integer regions as the ``(n, 5)`` int64 table ``par_spectral_process_f32`` takes, or None if a
+    region does not fit the device operator's contract (outside the spectrogram, thinner than two bins)."""
+    n_frames = (n + fft_size // 2) // hop + 1
+    regs = np.array([marker_region(d, sr, fft_size, hop) for d in drops], dtype=np.int64).reshape(-1, 5)
+    for frame_b, frame_a, around, bin_l, bin_u in regs:
+        if frame_b < 0 or frame_a <= frame_b or frame_a > n_frames or around < 1 or bin_u - bin_l < 2 or bin_u > fft_size // 2 + 1:
+            return None
+    return regs
+
+
+def heal(signal, sr, drops, fft_size=512, hop=32, channels=None, on_device=True):
     """Repair marked dropouts (dropout_healer_gui.py:111-166): per channel STFT, interpolate the
     magnitude across every marker from its surroundings, inverse STFT.  ``signal`` is
     ``(frames, channels)``; returns the same shape and dtype (untouched channels are left as the
-    reference leaves them: uninitialised there, copied through here)."""
+    reference leaves them: uninitialised there, copied through here).
+
+    The whole chain -- pad, transform, per-marker gain, inverse transform -- runs on the device in one call
+    (``fourier.stft_mask_istft``: one upload, one download, the spectrogram never visits the host).
+    ``on_device=False``, or a marker that does not fit the device operator, takes the transforms to the device but
+    builds the gain mask with numpy/scipy on the host exactly like the reference (``heal_gain_db``)."""
     signal = np.asarray(signal)
     if signal.ndim == 1:
         signal = signal[:, None]
     n = len(signal)
     if channels is None:
         channels = range(signal.shape[1])
+    channels = list(channels)
     output = np.array(signal, copy=True)
+    regs = _device_regions(drops, sr, fft_size, hop, n) if on_device else None
+    if regs is not None and channels:
+        healed = fourier.stft_mask_istft(signal[:, channels], "heal", fft_size, hop, params=regs)
+        output[:, channels] = healed
+        return output
     y_pad = fourier.fix_length(signal, n + fft_size // 2, axis=0)
     for channel in channels:
         spectrum = np.array(fourier.stft(y_pad[:, channel], n_fft=fft_size, step=hop))
@@ -145,19 +168,40 @@ def locate(magnitude, sr, fft_size, hop, t_0, t_1, f_lower, f_upper, sensitivity
     return peaks, found
 
 
-def max_mono(signal, fft_size=512, hop=32):
+def max_mono(signal, fft_size=512, hop=32, on_device=True):
     """dropouts_gui.py:137-163: per time-frequency cell keep the louder (``max``) or the quieter
-    (``min``) of the two channels of a stereo take.  Returns ``{"max": y, "min": y}``."""
+    (``min``) of the two channels of a stereo take.  Returns ``{"max": y, "min": y}``.  One device call: both
+    channels are transformed once, both selections are made and inverted there (``on_device=False``: select on the
+    host between a device STFT and two device iSTFTs, like the reference)."""
     signal = np.asarray(signal)
     if signal.ndim != 2 or signal.shape[1] != 2:
         raise ValueError("expects stereo input")
     n = len(signal)
+    if on_device:
+        both = fourier.stft_mask_istft(signal, "max_min", fft_size, hop)
+        return {"max": np.ascontiguousarray(both[:, 0]), "min": np.ascontiguousarray(both[:, 1])}
     y_pad = fourier.fix_length(signal, n + fft_size // 2, axis=0)
     left, right = (np.array(s) for s in fourier.stft_multi(y_pad, n_fft=fft_size, step=hop))
     out = {}
     for name, mask in (("max", np.abs(left) > np.abs(right)), ("min", np.abs(left) < np.abs(right))):
         out[name] = fourier.istft(np.where(mask, left, right), length=n, hop_length=hop)
     return out
+
+
+def noise_gate(signal, profile_db, gain_db, fft_size=512, hop=32, channels=None):
+    """The spectral gate of renoiser_gui.py:273-278 + :303-319 (get_mask_fac / run_resample): every cell whose level
+    ``to_dB(|S| + 1e-7)`` does not exceed ``profile_db[bin]`` (the tool's ``final_profile``: noise profile + gain +
+    control curve + overhead) is scaled by ``to_fac(gain_db)``; all on the device in one call.  ``signal`` is
+    ``(frames, channels)``; returns ``(frames, len(channels))`` float32."""
+    signal = np.asarray(signal)
+    if signal.ndim == 1:
+        signal = signal[:, None]
+    if channels is None:
+        channels = range(signal.shape[1])
+    profile_db = np.asarray(profile_db, dtype=np.float64)
+    if profile_db.shape != (fft_size // 2 + 1,):
+        raise ValueError("profile_db needs one level per bin")
+    return fourier.stft_mask_istft(signal[:, list(channels)], "gate", fft_size, hop, params=profile_db, gain_db=gain_db)
 
 
 def heuristic_band_peaks(imdata_db, sr, fft_size, f_lower=100, f_upper=15000, num_bands=5):

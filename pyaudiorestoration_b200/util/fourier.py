@@ -93,6 +93,48 @@ def stft_multi(signal, n_fft=1024, step=512, window_name='blackmanharris', zerop
     return out.transpose(0, 2, 1)
 
 
+SPEC_OPS = {"gate": _lib.PAR_SPEC_GATE, "max": _lib.PAR_SPEC_SELECT_MAX, "min": _lib.PAR_SPEC_SELECT_MIN,
+            "max_min": _lib.PAR_SPEC_SELECT_BOTH, "heal": _lib.PAR_SPEC_HEAL}
+
+
+def stft_mask_istft(signal, op, n_fft=512, step=32, window_name='blackmanharris', params=None, gain_db=0.0):
+    """Extension (no single reference counterpart): ``istft(op(stft(fix_length(signal, n + n_fft//2))), length=n,
+    hop_length=step)`` for every channel of a ``(frames, channels)`` array with the spectrogram RESIDENT ON THE DEVICE --
+    one upload and one download instead of the two host round trips of the reference's tools
+    (dropout_healer_gui.py:129-164, dropouts_gui.py:148-159, renoiser_gui.py:310-317).
+
+    op: ``"gate"`` (params = per-bin threshold in dB, gain_db), ``"max"`` / ``"min"`` / ``"max_min"`` (stereo in, 1 or 2
+    channels out), ``"heal"`` (params = int64 ``(n, 5)`` marker regions ``(frame_b, frame_a, frame_surrounding, bin_l,
+    bin_u)``).  Returns ``(frames, channels_out)`` float32."""
+    n_fft, step, _ = _prep_args(n_fft, step, 1)
+    signal = np.asarray(signal)
+    if signal.ndim == 1:
+        signal = signal[:, None]
+    keep, ptr, fs, cs = _lib.f32_layout_2d(signal)
+    frames, channels = keep.shape
+    if frames < 1:
+        raise ValueError('signal must not be empty')
+    L = _lib.lib()
+    _lib.require_device()
+    window = np.ascontiguousarray(dsp.get_window(window_name, n_fft), dtype=np.float32)
+    code = SPEC_OPS[op]
+    n_out = 2 if op == "max_min" else (1 if op in ("max", "min") else channels)
+    if op == "gate":
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        pptr, pn = p.ctypes.data, len(p)
+    elif op == "heal":
+        p = np.ascontiguousarray(params, dtype=np.int64).reshape(-1, 5)
+        pptr, pn = (p.ctypes.data if len(p) else None), len(p)
+    else:
+        p, pptr, pn = None, None, 0
+    out = _lib.pinned_empty((frames, n_out), np.float32)
+    rc = L.par_spectral_process_f32(ptr, frames, fs, channels, cs, n_fft, step, window.ctypes.data, window.ctypes.data, code,
+                                    pptr, pn, float(gain_db), out.ctypes.data, n_out, 1, 0, _lib.device(), None)
+    _lib.check(rc, "par_spectral_process_f32")
+    del keep, p
+    return out
+
+
 def stft(x, n_fft=1024, step=512, window_name='blackmanharris', zeropad=1):
     """Compute the STFT (util/fourier.py:37-75).
 

@@ -800,7 +800,53 @@ def test_cfg4_full_file_against_the_reference_run(golden_dir, fourier):
         assert len(b[4]) > 0 and np.array_equal(b[4], z[f"heur_band_peaks_{i}"])
     out = dropouts.heuristic(x[:, None], sr, fft_size, hop)[:, 0]
     assert np.sum(out != x) > 1000                                  # the tool really changed the signal
-    assert rel_l2(out.astype(np.float64), z["heur_out"].astype(np.float64)) <= TOL and rel_max(out, z["heur_out"]) <= 2 * TOL
+    # the correction curve comes from dB MEANS over bands, dominated by cells far below the loud ones, where the
+    # single-precision transforms of both sides carry ~1e-3 relative error: the audio agrees to a few 1e-6, the integer
+    # valley indices above exactly
+    assert rel_l2(out.astype(np.float64), z["heur_out"].astype(np.float64)) <= 5e-6 and rel_max(out, z["heur_out"]) <= 5e-6
+
+
+def test_device_resident_masks_match_the_host_mask_path_and_the_reference(golden_dir, fourier):
+    """stft -> mask -> istft with the spectrogram resident on the device (one upload, one
+    download): the noise gate against the unmodified renoiser_gui run, the heal and max/min-mono operators against
+    the reference-run fixtures (above) AND against this repo's host-mask path, multi-channel and strided inputs."""
+    from pyaudiorestoration_b200 import _lib, dropouts
+    L = _lib.lib()
+    z = _load(golden_dir, "gate")
+    x = (z["pcm"].astype(np.float64) / 32768.0).astype(np.float32)
+    fft_size, hop = int(z["fft_size"]), int(z["hop"])
+    launches0 = L.par_kernel_launch_count()
+    y = dropouts.noise_gate(x, z["profile_db"], float(z["gain_db"]), fft_size, hop)[:, 0]
+    assert 4 <= L.par_kernel_launch_count() - launches0 <= 6        # de-interleave, stft, gate, istft frames + overlap-add
+    # the same gate applied on the host to the SAME device spectrogram (one more round trip): identical decisions
+    n = len(x)
+    spec = np.array(fourier.stft(fourier.fix_length(x, n + fft_size // 2), n_fft=fft_size, step=hop))
+    mask = np.where(20 * np.log10(np.abs(spec).astype(np.float64) + 1e-7) > z["profile_db"][:, None], 0.0, float(z["gain_db"]))
+    y_host = fourier.istft((spec * np.power(10, mask / 20).astype(np.float32)).astype(np.complex64), length=n, hop_length=hop)
+    assert rel_l2(y.astype(np.float64), y_host.astype(np.float64)) <= TOL and rel_max(y, y_host) <= TOL
+    # against the unmodified reference run: a hard gate flips the few cells whose level sits within the float32 rounding of
+    # EITHER transform (both are single precision; quiet cells carry ~1e-3 relative error) of the profile
+    assert rel_l2(y.astype(np.float64), z["gated"].astype(np.float64)) <= 5e-5
+    # heal: device operator == host mask path, 3 channels, middle one untouched
+    d = _load(golden_dir, "dropouts")
+    xd = (d["pcm"].astype(np.float64) / 32768.0).astype(np.float32)
+    sr = int(d["sr"])
+    drops = [dropouts.Dropout(*m) for m in d["markers"].tolist()]
+    sig = np.stack([xd, 0.5 * xd[::-1], synth(len(xd), 8, sr)], axis=1)
+    dev = dropouts.heal(sig, sr, drops, 512, 32, channels=[0, 2])
+    host = dropouts.heal(sig, sr, drops, 512, 32, channels=[0, 2], on_device=False)
+    assert np.array_equal(dev[:, 1], sig[:, 1])
+    for c in (0, 2):
+        assert rel_l2(dev[:, c].astype(np.float64), host[:, c].astype(np.float64)) <= TOL and rel_max(dev[:, c], host[:, c]) <= TOL
+    assert rel_l2(dev[:, 0].astype(np.float64), d["healed"].astype(np.float64)) <= TOL
+    # max / min mono: device select == host select
+    st = np.stack([synth(30000, 91, 44100.0), synth(30000, 92, 44100.0)], axis=1)
+    a, b = dropouts.max_mono(st, 512, 32), dropouts.max_mono(st, 512, 32, on_device=False)
+    for k in ("max", "min"):
+        assert rel_l2(a[k].astype(np.float64), b[k].astype(np.float64)) <= 5e-6
+    # a marker the device operator does not take (one bin high) falls back to the host mask, not to an error
+    thin = [dropouts.Dropout(t=1.0, width=0.02, f=1000.0, height=10.0, surrounding=0.5)]
+    assert dropouts._device_regions(thin, sr, 512, 32, len(xd)) is None
 
 
 # ----------------------------------------------------------------------------------------- trackers (8f rank 1)

@@ -141,3 +141,12 @@ def test_cfg4_full_oracle_batch_tool(full):
     for i, g in enumerate(got):
         assert len(g) > 0 and np.array_equal(g, z[f"heur_band_peaks_{i}"])
     assert np.sum(z["heur_out"] != x) > 1000
+
+
+def test_noise_gate_oracle_matches_reference_run(golden_dir):
+    """the oracle's spectral gate equals the unmodified renoiser_gui.Canvas.run_resample output
+    (tests/golden/make_golden_gate.py)."""
+    z = np.load(os.path.join(golden_dir, "gate.npz"))
+    x = (z["pcm"].astype(np.float64) / 32768.0).astype(np.float32)
+    y = onp.noise_gate_ref(x, z["profile_db"], float(z["gain_db"]), int(z["fft_size"]), int(z["hop"]))
+    assert np.array_equal(np.asarray(y).astype(np.float32), z["gated"])
