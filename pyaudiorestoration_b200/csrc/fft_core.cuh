@@ -50,6 +50,13 @@ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 	return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
+// to_mag (util/fourier.py:23-24): |z| + 1e-7.  One MUFU square root (relative error 2^-23) instead of the
+// IEEE-rounded sequence: the magnitude epilogue must not cost more than the complex one it halves.
+__device__ __forceinline__ float cmag(float2 z) {
+	float r;
+	asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(z.x, z.x, z.y * z.y)));
+	return r + 1e-7f;
+}
 // a * w for forward transforms, a * conj(w) for inverse ones (tables hold forward twiddles)
 template <bool INV>
 __device__ __forceinline__ float2 ctw(float2 a, float2 w) {

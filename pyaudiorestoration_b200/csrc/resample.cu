@@ -345,8 +345,7 @@ sinc_kernel(const __grid_constant__ SincArgs a, const __grid_constant__ SincTab<
 	}
 
 	// positions of work item w -> tb[buf].pos (asynchronous)
-	auto prefetch_pos = [&](int64_t w, int buf) {
-		const int64_t tile = w % tiles;
+	auto prefetch_pos = [&](int64_t tile, int buf) {
 		const int64_t i0 = a.out_begin + tile * SINC_TILE;
 		int64_t cnt = a.m - i0;
 		if (cnt > SINC_TILE + 1) cnt = SINC_TILE + 1;
@@ -354,11 +353,9 @@ sinc_kernel(const __grid_constant__ SincArgs a, const __grid_constant__ SincTab<
 	};
 
 	// set-up of work item w from tb[buf].pos: per-output records, span, units; returns the tile description
-	auto prepare = [&](int64_t w, int buf) -> SincTileInfo {
+	auto prepare = [&](int grp, int64_t tile, int buf) -> SincTileInfo {
 		SincTileBuf &tb = sm.tb[buf];
 		SincTileInfo ti;
-		const int grp = (int)(w / tiles);
-		const int64_t tile = w - (int64_t)grp * tiles;
 		ti.ch0 = grp * CH;
 		ti.i0 = a.out_begin + tile * SINC_TILE;
 		double rf = rint(tb.pos[0]);
@@ -465,22 +462,41 @@ sinc_kernel(const __grid_constant__ SincArgs a, const __grid_constant__ SincTab<
 		for (int c = 0; c < CH; c++) {
 			const bool have = ti.ch0 + c < a.n_ch;
 			const float *src = a.signal + (int64_t)(ti.ch0 + c) * a.sig_ch_stride + (ti.tlo - a.sig_origin) * a.sig_stride;
-			for (int e = tid; e < len; e += SINC_THREADS) {
-				const int P = e + SINC_XFRONT;
-				float *dst = xs + (P & 1) * plane + (P >> 1) * CH + c;
-				if (have && e < ti.span) cp_async4(dst, src + (int64_t)e * a.sig_stride);
-				else *dst = 0.f;
+			// element e -> parity plane (e & 1), slot (e + XFRONT) >> 1; two elements per thread and round
+			float *d0 = xs + ((SINC_XFRONT >> 1) + tid) * CH + c, *d1 = d0 + plane;
+			const int span = have ? ti.span : 0;
+			if (a.sig_stride == 1) {
+				const float *sp = src + 2 * tid;
+				for (int e = 2 * tid; e < len; e += 2 * SINC_THREADS, sp += 2 * SINC_THREADS, d0 += SINC_THREADS * CH, d1 += SINC_THREADS * CH) {
+					if (e < span) cp_async4(d0, sp); else *d0 = 0.f;
+					if (e + 1 < span) cp_async4(d1, sp + 1); else *d1 = 0.f;
+				}
+			} else {
+				for (int e = 2 * tid; e < len; e += 2 * SINC_THREADS, d0 += SINC_THREADS * CH, d1 += SINC_THREADS * CH) {
+					if (e < span) cp_async4(d0, src + (int64_t)e * a.sig_stride); else *d0 = 0.f;
+					if (e + 1 < span) cp_async4(d1, src + (int64_t)(e + 1) * a.sig_stride); else *d1 = 0.f;
+				}
 			}
 		}
 	};
 
-	prefetch_pos(w0, 0);
+	// (group, tile) of the work items w, w + 1, w + 2, advanced without 64-bit divisions
+	int grp0 = (int)(w0 / tiles);
+	int64_t tile0 = w0 - (int64_t)grp0 * tiles;
+	auto advance = [&](int &g, int64_t &t) { if (++t == tiles) { t = 0; g++; } };
+	int grp1 = grp0, grp2;
+	int64_t tile1 = tile0, tile2;
+	advance(grp1, tile1);
+	grp2 = grp1; tile2 = tile1;
+	advance(grp2, tile2);
+
+	prefetch_pos(tile0, 0);
 	cp_async_commit();
 	cp_async_wait_all();
 	__syncthreads();
-	SincTileInfo cur = prepare(w0, 0);
+	SincTileInfo cur = prepare(grp0, tile0, 0);
 	stage_span(cur, 0);
-	if (w0 + 1 < w1) prefetch_pos(w0 + 1, 1);
+	if (w0 + 1 < w1) prefetch_pos(tile1, 1);
 	cp_async_commit();
 
 	for (int64_t w = w0; w < w1; w++) {
@@ -489,11 +505,13 @@ sinc_kernel(const __grid_constant__ SincArgs a, const __grid_constant__ SincTab<
 		__syncthreads();
 		SincTileInfo nxt = cur;
 		if (w + 1 < w1) {
-			nxt = prepare(w + 1, buf ^ 1);
+			nxt = prepare(grp1, tile1, buf ^ 1);
 			stage_span(nxt, buf ^ 1);
-			if (w + 2 < w1) prefetch_pos(w + 2, buf);     // tb[buf].pos is no longer needed
+			if (w + 2 < w1) prefetch_pos(tile2, buf);     // tb[buf].pos is no longer needed
 			cp_async_commit();
 		}
+		grp1 = grp2; tile1 = tile2;
+		advance(grp2, tile2);
 		__syncthreads();                // unit table of the next tile / of the first tile complete
 		const SincTileBuf &tb = sm.tb[buf];
 		const float *xs = xs_all + buf * CH * xpitch;

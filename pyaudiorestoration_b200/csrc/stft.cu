@@ -133,8 +133,8 @@ stft_kernel(StftArgs a, const float2 *__restrict__ tw, float half_scale) {
 				const float2 xb = make_float2((ex - wo.x) * half_scale, (wo.y - ey) * half_scale);
 				if (MAG) {
 					float *o = reinterpret_cast<float *>(a.out) + row;
-					o[k] = sqrtf(fmaf(xa.x, xa.x, xa.y * xa.y)) + 1e-7f;
-					if (k != S::M - k) o[S::M - k] = sqrtf(fmaf(xb.x, xb.x, xb.y * xb.y)) + 1e-7f;
+					o[k] = cmag(xa);
+					if (k != S::M - k) o[S::M - k] = cmag(xb);
 				} else {
 					float2 *o = reinterpret_cast<float2 *>(a.out) + row;
 					o[k] = xa;
@@ -308,8 +308,8 @@ stft_tma_kernel(StftArgs a, const float2 *__restrict__ tw, float half_scale) {
 			const float2 xb = make_float2((ex - wo.x) * half_scale, (wo.y - ey) * half_scale);
 			if (MAG) {
 				float *o = reinterpret_cast<float *>(a.out) + row;
-				o[k] = sqrtf(fmaf(xa.x, xa.x, xa.y * xa.y)) + 1e-7f;
-				if (both) o[S::M - k] = sqrtf(fmaf(xb.x, xb.x, xb.y * xb.y)) + 1e-7f;
+				o[k] = cmag(xa);
+				if (both) o[S::M - k] = cmag(xb);
 			} else {
 				float2 *o = reinterpret_cast<float2 *>(a.out) + row;
 				o[k] = xa;

@@ -160,8 +160,8 @@ stft_large_rows_kernel(StftArgs a, int log2m1, int64_t batch0, const float2 *__r
 		const float2 xb = make_float2((ex - wo.x) * half_scale, (wo.y - ey) * half_scale);
 		if (MAG) {
 			float *o = reinterpret_cast<float *>(a.out) + row;
-			o[k] = sqrtf(fmaf(xa.x, xa.x, xa.y * xa.y)) + 1e-7f;
-			if (k != M - k) o[M - k] = sqrtf(fmaf(xb.x, xb.x, xb.y * xb.y)) + 1e-7f;
+			o[k] = cmag(xa);
+			if (k != M - k) o[M - k] = cmag(xb);
 		} else {
 			float2 *o = reinterpret_cast<float2 *>(a.out) + row;
 			o[k] = xa;

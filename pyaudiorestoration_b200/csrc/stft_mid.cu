@@ -175,8 +175,8 @@ stft_mid_kernel(StftArgs a, const float2 *__restrict__ tw1, const float2 *__rest
 			const float2 xb = make_float2((ex - wo.x) * half_scale, (wo.y - ey) * half_scale);
 			if (MAG) {
 				float *o = reinterpret_cast<float *>(a.out) + orow;
-				o[k] = sqrtf(fmaf(xa.x, xa.x, xa.y * xa.y)) + 1e-7f;
-				if (k != C::M - k) o[C::M - k] = sqrtf(fmaf(xb.x, xb.x, xb.y * xb.y)) + 1e-7f;
+				o[k] = cmag(xa);
+				if (k != C::M - k) o[C::M - k] = cmag(xb);
 			} else {
 				float2 *o = reinterpret_cast<float2 *>(a.out) + orow;
 				o[k] = xa;
