@@ -381,11 +381,20 @@ def run_cfg3_strong(torch, dist, rank, world, dev, steps, workload="cfg3"):
     pos_buf = torch.empty(int((sh.s1 - sh.s0) * 1.1) + 8 * HOP, dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream(dev)
 
+    side = torch.cuda.Stream(dev)
+
     def step():
+        # order matters: the transform is a persistent kernel that fills every SM, so the two small collectives
+        # go first; the serial host chain of speed_to_pos and its copies then run on a side stream BEHIND the
+        # transform (its expansion kernel starts as the transform's CTAs retire)
         sh.exchange_halos(buf)
+        sums = sh.position_sums(st, sp, dev) if world > 1 else None
+        side.wait_stream(stream)
         sh.stft(buf, window, out=S_out)
-        ps, p0, m = sh.positions(st, sp, dev, out=pos_buf)
+        ps, p0, m = sh.positions(st, sp, dev, out=pos_buf, sums=sums, stream=side)
+        stream.wait_stream(side)
         y = sh.resample(buf, ps, "Sinc", pos_origin=p0, m=m)
+        side.wait_stream(stream)                     # the next step's positions overwrite pos_buf
         return y, m
 
     def barrier():

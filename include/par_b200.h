@@ -225,13 +225,16 @@ PAR_API int par_speed_to_pos_range_f64(const double *sampletimes, const double *
  * computes the totals of segments [seg_begin, seg_end) (sums[0] is segment seg_begin; device memory), the ranks
  * all-gather their slices (one small collective, done by the caller) and pass the totals of ALL k-1 segments as
  * seg_sums: no rank then repeats the divisions of the whole curve, and only the window's rows of the segment
- * tables are uploaded.  Results are bit-identical to par_speed_to_pos_range_f64. */
+ * tables are uploaded.  seg_n_out (HOST int64[k-1], may be NULL) receives the error-diffused segment lengths of the
+ * whole curve (par_speed_segments); passing them back as seg_n (may be NULL) saves the second evaluation of that
+ * serial recurrence.  Results are bit-identical to par_speed_to_pos_range_f64. */
 PAR_API int par_segment_sums_f64(const double *sampletimes, const double *speeds, int64_t k,
-                         int64_t seg_begin, int64_t seg_end, double *sums, unsigned flags, int device, void *stream);
+                         int64_t seg_begin, int64_t seg_end, double *sums, int64_t *seg_n_out, unsigned flags,
+                         int device, void *stream);
 PAR_API int par_speed_to_pos_range_sums_f64(const double *sampletimes, const double *speeds, int64_t k,
                                     double num_input_samples, double lo_pos, double hi_pos, const double *seg_sums,
-                                    double *pos, int64_t cap, int64_t *pos_origin, int64_t *pos_count,
-                                    int64_t *m, unsigned flags, int device, void *stream);
+                                    const int64_t *seg_n, double *pos, int64_t cap, int64_t *pos_origin,
+                                    int64_t *pos_count, int64_t *m, unsigned flags, int device, void *stream);
 
 /* par_resample_range_f32: outputs [out_begin, out_end) of util/resampling.py:51-90 / :228-229 over
  * m_global read positions.  pos holds positions [pos_origin, pos_origin + pos_count) and must reach

@@ -81,9 +81,9 @@ def _declare(L):
     L.par_spectral_process_f32.restype = i32
     L.par_spectral_process_f32.argtypes = [vp, i64, i64, i32, i64, i32, i32, vp, vp, i32, vp, i64, dbl, vp, i64, i64, u32, i32, vp]
     L.par_segment_sums_f64.restype = i32
-    L.par_segment_sums_f64.argtypes = [vp, vp, i64, i64, i64, vp, u32, i32, vp]
+    L.par_segment_sums_f64.argtypes = [vp, vp, i64, i64, i64, vp, vp, u32, i32, vp]
     L.par_speed_to_pos_range_sums_f64.restype = i32
-    L.par_speed_to_pos_range_sums_f64.argtypes = [vp, vp, i64, dbl, dbl, dbl, vp, vp, i64, vp, vp, vp, u32, i32, vp]
+    L.par_speed_to_pos_range_sums_f64.argtypes = [vp, vp, i64, dbl, dbl, dbl, vp, vp, vp, i64, vp, vp, vp, u32, i32, vp]
     L.par_trace_f32.restype = i32
     L.par_trace_f32.argtypes = [vp, i32, i64, i64, i64, i64, i32, dbl, dbl, i32, vp, u32, i32, vp]
     L.par_stft_trace_f32.restype = i32

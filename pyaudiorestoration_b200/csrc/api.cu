@@ -938,8 +938,8 @@ extern "C" PAR_API int par_speed_to_pos_range_f64(const double *sampletimes, con
 // util/resampling.py:120-126 that a rank of a time-sharded job contributes (dist.TimeShard.positions
 // all-gathers the slices and hands the whole array to par_speed_to_pos_range_sums_f64).
 extern "C" PAR_API int par_segment_sums_f64(const double *sampletimes, const double *speeds, int64_t k,
-                                            int64_t seg_begin, int64_t seg_end, double *sums, unsigned flags,
-                                            int device, void *stream) {
+                                            int64_t seg_begin, int64_t seg_end, double *sums, int64_t *seg_n_out,
+                                            unsigned flags, int device, void *stream) {
 	if (!(flags & PAR_DEVICE_PTRS)) { set_error("segment_sums: device pointers only"); return PAR_EUNSUPPORTED; }
 	if (!sampletimes || !speeds || k < 2 || seg_begin < 0 || seg_end < seg_begin || seg_end > k - 1 || (!sums && seg_end > seg_begin)) {
 		set_error("segment_sums: bad argument");
@@ -950,14 +950,18 @@ extern "C" PAR_API int par_segment_sums_f64(const double *sampletimes, const dou
 	const int64_t cnt = seg_end - seg_begin;
 	if (cnt == 0) return PAR_OK;
 	cudaStream_t st = (cudaStream_t)stream;
-	std::vector<int64_t> seg_n(k - 1);
-	if ((rc = par_speed_segments(sampletimes, speeds, k, seg_n.data(), nullptr)) != PAR_OK) return rc;
+	// the error-diffused segment lengths of the WHOLE curve (a serial host recurrence); handed back so that the
+	// caller's next step does not repeat it
+	std::vector<int64_t> seg_local;
+	int64_t *seg_n = seg_n_out;
+	if (!seg_n) { seg_local.resize(k - 1); seg_n = seg_local.data(); }
+	if ((rc = par_speed_segments(sampletimes, speeds, k, seg_n, nullptr)) != PAR_OK) return rc;
 	char *pin = g_pinned.get(((size_t)cnt * 2 + 1) * 8);
 	if (!pin) { set_error("segment_sums: pinned staging allocation failed"); return PAR_ECUDA; }
 	double *h_sp = (double *)pin;
 	int64_t *h_n = (int64_t *)(h_sp + cnt + 1);
 	memcpy(h_sp, speeds + seg_begin, (size_t)(cnt + 1) * 8);
-	memcpy(h_n, seg_n.data() + seg_begin, (size_t)cnt * 8);
+	memcpy(h_n, seg_n + seg_begin, (size_t)cnt * 8);
 	DevBuf d_tab(st);
 	if ((rc = d_tab.alloc(((size_t)cnt * 2 + 1) * 8)) != PAR_OK) return rc;
 	PAR_CUDA(cudaMemcpyAsync(d_tab.p, pin, ((size_t)cnt * 2 + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -969,7 +973,7 @@ extern "C" PAR_API int par_segment_sums_f64(const double *sampletimes, const dou
 
 extern "C" PAR_API int par_speed_to_pos_range_sums_f64(const double *sampletimes, const double *speeds, int64_t k,
                                                        double num_input_samples, double lo_pos, double hi_pos,
-                                                       const double *seg_sums, double *pos, int64_t cap,
+                                                       const double *seg_sums, const int64_t *seg_n_in, double *pos, int64_t cap,
                                                        int64_t *pos_origin, int64_t *pos_count, int64_t *m,
                                                        unsigned flags, int device, void *stream) {
 	if (!(flags & PAR_DEVICE_PTRS)) { set_error("speed_to_pos_range: device pointers only"); return PAR_EUNSUPPORTED; }
@@ -981,7 +985,11 @@ extern "C" PAR_API int par_speed_to_pos_range_sums_f64(const double *sampletimes
 	if (rc != PAR_OK) return rc;
 	std::vector<int64_t> seg_n(k - 1);
 	int64_t total = 0;
-	if ((rc = par_speed_segments(sampletimes, speeds, k, seg_n.data(), &total)) != PAR_OK) return rc;
+	if (seg_n_in) {
+		for (int64_t i = 0; i + 1 < k; i++) { seg_n[i] = seg_n_in[i]; if (seg_n_in[i] > 0) total += seg_n_in[i]; }
+	} else if ((rc = par_speed_segments(sampletimes, speeds, k, seg_n.data(), &total)) != PAR_OK) {
+		return rc;
+	}
 	const double window[2] = {lo_pos, hi_pos};
 	return positions_device(sampletimes, speeds, k, num_input_samples, seg_n, total, pos, cap, m, (cudaStream_t)stream,
 	                        nullptr, window, pos_origin, pos_count, seg_sums);

@@ -122,21 +122,50 @@ class TimeShard:
         a = min(self.rank * per, n_seg)
         return per, a, min(a + per, n_seg)
 
-    def positions(self, sampletimes, speeds, device, out=None, group=None, share_sums=True):
-        """This rank's slice of the read positions of a speed curve: the positions that fall into
-        ``[s0 - 1, s1 + 1]`` plus the segment after them.  Returns ``(pos_slice, pos_origin, m_global)``;
-        ``pos_slice[i]`` is position ``pos_origin + i``.
-
-        With several ranks (and ``share_sums``) the per-segment totals the serial offset chain needs are
-        computed once per JOB instead of once per rank: every rank sums its block of segments
-        (``par_segment_sums_f64``), one all-gather of ``8 * n_segments`` bytes shares them, and
-        ``par_speed_to_pos_range_sums_f64`` expands the rank's window.  Otherwise
-        ``par_speed_to_pos_range_f64`` does everything locally.  Both give identical bits."""
+    def position_sums(self, sampletimes, speeds, device, group=None):
+        """First half of the shared-sums positions: this rank's block of per-segment totals
+        (``par_segment_sums_f64``) and ONE all-gather of ``8 * n_segments`` bytes.  Returns the handle
+        ``positions(..., sums=...)`` takes.  Splitting the call lets a caller enqueue other work (the STFT of the
+        step) between the collective and the serial host chain of the second half, which then hides behind it."""
         import torch
         import torch.distributed as dist
         L = _lib.lib()
         st = np.ascontiguousarray(sampletimes, dtype=np.float64)
         sp = np.ascontiguousarray(speeds, dtype=np.float64)
+        n_seg = len(st) - 1
+        per, a, b = self.segment_slice(n_seg)
+        dev = torch.device(device)
+        mine = torch.zeros(per, dtype=torch.float64, device=dev)
+        seg_n = np.empty(n_seg, dtype=np.int64)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = L.par_segment_sums_f64(st.ctypes.data, sp.ctypes.data, len(st), a, b, mine.data_ptr(), seg_n.ctypes.data,
+                                    _lib.PAR_DEVICE_PTRS, dev.index, stream)
+        _lib.check(rc, "par_segment_sums_f64")
+        sums = torch.empty(per * self.world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(sums, mine, group=group)
+        return {"sums": sums, "seg_n": seg_n, "st": st, "sp": sp}
+
+    def positions(self, sampletimes, speeds, device, out=None, group=None, share_sums=True, sums=None, stream=None):
+        """This rank's slice of the read positions of a speed curve: the positions that fall into
+        ``[s0 - 1, s1 + 1]`` plus the segment after them.  Returns ``(pos_slice, pos_origin, m_global)``;
+        ``pos_slice[i]`` is position ``pos_origin + i``.
+
+        With several ranks (and ``share_sums``) the per-segment totals the serial offset chain needs are
+        computed once per JOB instead of once per rank: every rank sums its block of segments, one all-gather
+        shares them (``position_sums``; pass its result as ``sums`` to split the call), and
+        ``par_speed_to_pos_range_sums_f64`` expands the rank's window.  Otherwise ``par_speed_to_pos_range_f64``
+        does everything locally.  Both give identical bits.  ``stream``: a torch stream for the second half (its
+        copies, its two synchronisations and the expansion kernel); default the current stream."""
+        import torch
+        import torch.distributed as dist
+        L = _lib.lib()
+        if sums is None and share_sums and self.world > 1 and dist.is_initialized():
+            sums = self.position_sums(sampletimes, speeds, device, group=group)
+        if sums is not None:
+            st, sp = sums["st"], sums["sp"]
+        else:
+            st = np.ascontiguousarray(sampletimes, dtype=np.float64)
+            sp = np.ascontiguousarray(speeds, dtype=np.float64)
         if out is None:
             # a chunk read at >= 0.5x speed yields at most 2x its length in outputs (+ 2 segments of slack)
             out = torch.empty(2 * (self.s1 - self.s0) + 4 * int(np.max(np.diff(st)) * 2 + 16), dtype=torch.float64,
@@ -144,25 +173,17 @@ class TimeShard:
         box = np.zeros(3, dtype=np.int64)
         lo = -np.inf if self.rank == 0 else float(self.s0) - 1.0
         hi = np.inf if self.rank == self.world - 1 else float(self.s1) + 1.0
-        stream = torch.cuda.current_stream(out.device).cuda_stream
-        if share_sums and self.world > 1 and dist.is_initialized():
-            n_seg = len(st) - 1
-            per, a, b = self.segment_slice(n_seg)
-            mine = torch.zeros(per, dtype=torch.float64, device=out.device)
-            rc = L.par_segment_sums_f64(st.ctypes.data, sp.ctypes.data, len(st), a, b, mine.data_ptr(), _lib.PAR_DEVICE_PTRS,
-                                        out.device.index, stream)
-            _lib.check(rc, "par_segment_sums_f64")
-            sums = torch.empty(per * self.world, dtype=torch.float64, device=out.device)
-            dist.all_gather_into_tensor(sums, mine, group=group)
+        cu = (stream if stream is not None else torch.cuda.current_stream(out.device)).cuda_stream
+        if sums is not None:
             rc = L.par_speed_to_pos_range_sums_f64(st.ctypes.data, sp.ctypes.data, len(st), float(self.n), lo, hi,
-                                                   sums.data_ptr(), out.data_ptr(), out.numel(), box[0:].ctypes.data,
-                                                   box[1:].ctypes.data, box[2:].ctypes.data, _lib.PAR_DEVICE_PTRS,
-                                                   out.device.index, stream)
+                                                   sums["sums"].data_ptr(), sums["seg_n"].ctypes.data, out.data_ptr(),
+                                                   out.numel(), box[0:].ctypes.data, box[1:].ctypes.data,
+                                                   box[2:].ctypes.data, _lib.PAR_DEVICE_PTRS, out.device.index, cu)
             _lib.check(rc, "par_speed_to_pos_range_sums_f64")
         else:
             rc = L.par_speed_to_pos_range_f64(st.ctypes.data, sp.ctypes.data, len(st), float(self.n), lo, hi, out.data_ptr(),
                                               out.numel(), box[0:].ctypes.data, box[1:].ctypes.data, box[2:].ctypes.data,
-                                              _lib.PAR_DEVICE_PTRS, out.device.index, stream)
+                                              _lib.PAR_DEVICE_PTRS, out.device.index, cu)
             _lib.check(rc, "par_speed_to_pos_range_f64")
         return out[:int(box[1])], int(box[0]), int(box[2])
 

@@ -97,6 +97,42 @@ class AbiDouble:
             _view(_ptr(y) + 4 * c * y_ch_stride, np.float32, (length,), (y_stride,))[...] = seg.astype(np.float32)
         return 0
 
+    def par_spectral_process_f32(self, x, n, x_stride, n_ch, x_ch_stride, n_fft, hop, window, syn_window, op, params,
+                                 n_params, gain_db, y, y_stride, y_ch_stride, flags, device, stream):
+        """stft -> mask -> istft of include/par_b200.h, with the oracle's transforms and float64 masks."""
+        self.calls.append(("par_spectral_process_f32", n, x_stride, n_ch, x_ch_stride, n_fft, hop, op, n_params, y_stride,
+                           y_ch_stride))
+        F = n_fft // 2 + 1
+        specs = []
+        for c in range(n_ch):
+            xc = np.ascontiguousarray(_view(_ptr(x) + 4 * c * x_ch_stride, np.float32, (n,), (x_stride,)))
+            pad = onp.fix_length(xc, n + n_fft // 2)
+            specs.append(np.array(onp.stft_f64(pad, n_fft, hop)).T)                  # (F, T) complex128
+        db = lambda s_: 20 * np.log10(np.abs(s_) + 1e-7)                              # noqa: E731
+        if op == 0:                                                                   # gate
+            thr = _view(_ptr(params), np.float64, (F,), (1,))
+            outs = [s_ * np.where(db(s_) > thr[:, None], 1.0, np.float32(10 ** (gain_db / 20))) for s_ in specs]
+        elif op in (1, 2, 3):                                                         # select max / min / both
+            l, r = specs
+            mx, mn = np.where(np.abs(l) > np.abs(r), l, r), np.where(np.abs(l) < np.abs(r), l, r)
+            outs = [mx] if op == 1 else ([mn] if op == 2 else [mx, mn])
+        else:                                                                         # heal
+            regs = _view(_ptr(params), np.int64, (n_params, 5), (5, 1)) if n_params else np.zeros((0, 5), np.int64)
+            outs = []
+            for s_ in specs:
+                d, gain = db(s_), np.zeros(s_.shape)
+                for fb, fa, ar, bl, bu in regs:
+                    before, after = np.mean(d[bl:bu, fb - ar:fb], axis=1), np.mean(d[bl:bu, fa:fa + ar], axis=1)
+                    yv = (np.linspace(fb, fa, num=fa - fb) - fb) / (fa - fb)
+                    target = before[:, None] * (1 - yv)[None, :] + after[:, None] * yv[None, :]
+                    boost = np.clip(target - d[bl:bu, fb:fa], gain[bl:bu, fb:fa], 255)
+                    gain[bl:bu, fb:fa] = boost
+                outs.append(s_ * 10 ** (gain / 20))
+        for c, s_ in enumerate(outs):
+            yy = onp.istft_ref(s_, hop_length=hop, length=n)
+            _view(_ptr(y) + 4 * c * y_ch_stride, np.float32, (n,), (y_stride,))[...] = np.asarray(yy).astype(np.float32)
+        return 0
+
     def par_speed_to_pos_f64(self, st, sp, k, n_in, pos, cap, m, flags, device, stream):
         stv = _view(_ptr(st), np.float64, (k,), (1,))
         spv = _view(_ptr(sp), np.float64, (k,), (1,))

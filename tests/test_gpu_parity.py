@@ -654,8 +654,10 @@ def test_shared_segment_sums_give_the_same_position_slices(par, resampling):
         sums = torch.zeros(per * world, dtype=torch.float64, device=dev)
         for r in range(world):
             a, b = min(r * per, n_seg), min(r * per + per, n_seg)
+            seg_n = np.empty(n_seg, dtype=np.int64)
             _lib.check(L.par_segment_sums_f64(st.ctypes.data, sp.ctypes.data, k, a, b, sums[r * per:].data_ptr(),
-                                              _lib.PAR_DEVICE_PTRS, dev.index, None), "par_segment_sums_f64")
+                                              seg_n.ctypes.data if r % 2 else None, _lib.PAR_DEVICE_PTRS, dev.index, None),
+                       "par_segment_sums_f64")
         bounds = np.linspace(0, n_in, world + 1)
         for r in range(world):
             lo = -np.inf if r == 0 else bounds[r] - 1.0
@@ -666,6 +668,7 @@ def test_shared_segment_sums_give_the_same_position_slices(par, resampling):
                 box = np.zeros(3, dtype=np.int64)
                 if shared:
                     rc = L.par_speed_to_pos_range_sums_f64(st.ctypes.data, sp.ctypes.data, k, float(n_in), lo, hi, sums.data_ptr(),
+                                                           seg_n.ctypes.data if r % 2 else None,
                                                            out.data_ptr(), out.numel(), box[0:].ctypes.data, box[1:].ctypes.data,
                                                            box[2:].ctypes.data, _lib.PAR_DEVICE_PTRS, dev.index, None)
                 else:
