@@ -565,7 +565,7 @@ PAR_API int par_istft_f32(const void *S, int n_fft, int64_t n_frames, int64_t s_
 	const float *dwin = device_window(device, window, n_fft, st);
 	if (!dwin) return PAR_ECUDA;
 	DevBuf frames(st);
-	if ((rc = frames.alloc((size_t)n_ch * n_frames * n_fft * sizeof(float))) != PAR_OK) return rc;
+	if (istft_needs_scratch(n_fft) && (rc = frames.alloc((size_t)n_ch * n_frames * n_fft * sizeof(float))) != PAR_OK) return rc;
 	IstftArgs a;
 	a.n_fft = n_fft; a.n_frames = n_frames; a.n_ch = n_ch; a.hop = hop; a.window = dwin;
 	a.start = start; a.length = length; a.frames = frames.as<float>();
@@ -681,7 +681,7 @@ PAR_API int par_spectral_process_f32(const float *x, int64_t n, int64_t x_stride
 	// ---- synthesis: istft(S, length=n, hop_length=hop), util/fourier.py:373-381 frame count
 	int64_t n_frames = (n + n_fft + hop - 1) / hop;
 	if (n_frames > T) n_frames = T;
-	if ((rc = dframes.alloc((size_t)n_out * n_frames * n_fft * sizeof(float))) != PAR_OK) return rc;
+	if (istft_needs_scratch(n_fft) && (rc = dframes.alloc((size_t)n_out * n_frames * n_fft * sizeof(float))) != PAR_OK) return rc;
 	IstftArgs ia;
 	ia.S = S; ia.n_fft = n_fft; ia.n_frames = n_frames; ia.s_pitch = F; ia.s_ch_stride = T * F; ia.n_ch = n_out; ia.hop = hop;
 	ia.window = dsyn; ia.start = n_fft / 2; ia.length = n; ia.frames = dframes.as<float>();

@@ -242,8 +242,16 @@ template <int TPF>
 struct SlotSync {
 	int id;
 	__device__ __forceinline__ void operator()() const {
-		if (TPF <= 32) __syncwarp();
-		else asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(TPF) : "memory");
+		if (TPF == 32) {
+			__syncwarp();
+		} else if (TPF < 32) {
+			// several slots share a warp and may run different numbers of frames: synchronise this slot's lanes only
+			const unsigned lane = threadIdx.x & 31u;
+			const unsigned mask = ((TPF >= 32 ? 0u : (1u << (TPF & 31))) - 1u) << (lane & ~(unsigned)(TPF - 1));
+			__syncwarp(mask);
+		} else {
+			asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(TPF) : "memory");
+		}
 	}
 };
 

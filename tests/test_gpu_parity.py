@@ -242,6 +242,40 @@ def test_stft_istft_round_trip(fourier, n_fft, hop):
     assert np.max(np.abs(y - x)) <= 1e-6 * np.max(np.abs(x)) * 2
 
 
+def test_istft_fused_equals_two_pass(par):
+    """The fused inverse transform + overlap-add (no scratch) and the frames-to-scratch + gather pair give identical
+    bits: both accumulate every output sample in ascending frame order.  Sizes with sub-warp slots (n_fft 64 ... 512),
+    one-warp and multi-warp slots, hop not dividing n_fft, several channels, short and over-long `length`."""
+    import subprocess
+    import sys
+    import textwrap
+    code = textwrap.dedent("""
+        import os, sys, numpy as np
+        sys.path.insert(0, %r)
+        from pyaudiorestoration_b200.util import fourier
+        rng = np.random.default_rng(3)
+        out = {}
+        for n_fft, hop, n in ((64, 16, 5000), (512, 32, 40000), (512, 96, 20011), (1024, 256, 50000), (4096, 1024, 120000),
+                              (16384, 4096, 200000), (32768, 8192, 150000)):
+            x = rng.standard_normal(n).astype(np.float32)
+            S = np.array(fourier.stft(fourier.fix_length(x, n + n_fft // 2), n_fft, hop))
+            out[f"{n_fft}_{hop}"] = fourier.istft(S, hop_length=hop, length=n)
+            out[f"{n_fft}_{hop}_long"] = fourier.istft(S, hop_length=hop, length=n + 3 * n_fft)
+            out[f"{n_fft}_{hop}_free"] = fourier.istft(S, hop_length=hop)
+        np.savez(sys.argv[1], **out)
+    """ % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        res = {}
+        for mode in ("0", "1"):
+            env = dict(os.environ, PAR_B200_ISTFT_TWO_PASS=mode)
+            path = os.path.join(d, f"r{mode}.npz")
+            subprocess.run([sys.executable, "-c", code, path], check=True, env=env)
+            res[mode] = np.load(path)
+        for k in res["0"].files:
+            assert np.array_equal(res["0"][k], res["1"][k]), k
+
+
 def test_istft_length_rules(fourier):
     x = synth(5000, 77)
     s = fourier.stft(x, 512, 128)
@@ -654,10 +688,12 @@ def test_shared_segment_sums_give_the_same_position_slices(par, resampling):
         sums = torch.zeros(per * world, dtype=torch.float64, device=dev)
         for r in range(world):
             a, b = min(r * per, n_seg), min(r * per + per, n_seg)
-            seg_n = np.empty(n_seg, dtype=np.int64)
+            got_n = np.empty(n_seg, dtype=np.int64)
             _lib.check(L.par_segment_sums_f64(st.ctypes.data, sp.ctypes.data, k, a, b, sums[r * per:].data_ptr(),
-                                              seg_n.ctypes.data if r % 2 else None, _lib.PAR_DEVICE_PTRS, dev.index, None),
+                                              got_n.ctypes.data if r % 2 else None, _lib.PAR_DEVICE_PTRS, dev.index, None),
                        "par_segment_sums_f64")
+            if r % 2:
+                seg_n = got_n                                  # the segment lengths come back from the call (optional)
         bounds = np.linspace(0, n_in, world + 1)
         for r in range(world):
             lo = -np.inf if r == 0 else bounds[r] - 1.0
