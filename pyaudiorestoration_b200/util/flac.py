@@ -1,5 +1,9 @@
 """A self-contained FLAC decoder (numpy + a tight Python loop over residual samples).
 
+Size and speed: the bit tables cover a bounded window of the file (~100 MB of memory however long it is), but the
+residual loop is Python: roughly 10 s of mono 44.1 kHz audio per second.  Fine for the reference's sample fixtures and
+short takes; ``util.io_ops.read_file`` uses ``soundfile`` instead whenever that package is importable.
+
 The reference reads audio through soundfile/libsndfile (util/io_ops.py:7-16), which is not available
 in this image; its sample fixtures (samples/*.flac) and the "*.flac *.wav" file dialogs of its tools
 need a decoder either side of the hot path.  Implements the FLAC format
@@ -40,32 +44,59 @@ def _crc16(data):
 
 
 class _Bits:
-    """Random-access bit view of a byte string: ``win[p]`` holds the 32 bits that start at bit p,
-    ``next_one[p]`` the position of the first 1 bit at or after p."""
+    """Bit reader over a byte string with a BOUNDED random-access window: for the bytes of the current window
+    ``win[p]`` holds the 32 bits that start at (window-relative) bit p and ``next_one[p]`` the position of the first
+    1 bit at or after p.  The window (``WINDOW`` bytes, ~64 bytes of tables per byte) is rebuilt when the cursor gets
+    near its end, so memory stays ~100 MB however long the file is; ``ensure`` makes room for a whole frame."""
+
+    WINDOW = 1 << 19
 
     def __init__(self, data):
-        raw = np.frombuffer(data, dtype=np.uint8)
-        self.nbits = len(raw) * 8
-        padded = np.concatenate([raw, np.zeros(8, np.uint8)])
-        # 40-bit big-endian window at every byte, then one shifted copy per bit offset
-        b = padded.astype(np.uint64)
+        self.data = data
+        self.nbits = len(data) * 8
+        self.pos = 0                 # absolute bit position
+        self.base = 0                # absolute bit position of window bit 0
+        self.limit = 0               # window length in bits that is safe to read 40 bits at
+        self._load(0, self.WINDOW)
+
+    def _load(self, byte0, nbytes):
+        raw = np.frombuffer(self.data, dtype=np.uint8, count=max(0, min(nbytes, len(self.data) - byte0)), offset=byte0)
         n = len(raw)
-        w40 = (b[0:n] << np.uint64(32)) | (b[1:n + 1] << np.uint64(24)) | (b[2:n + 2] << np.uint64(16)) | \
-              (b[3:n + 3] << np.uint64(8)) | b[4:n + 4]
-        win = np.empty((n, 8), dtype=np.uint64)
-        for s in range(8):
-            win[:, s] = (w40 >> np.uint64(8 - s)) & np.uint64(0xFFFFFFFF)
+        padded = np.concatenate([raw, np.zeros(8, np.uint8)]).astype(np.uint64)
+        # 40-bit big-endian window at every byte, then one shifted copy per bit offset
+        w40 = (padded[0:n] << np.uint64(32)) | (padded[1:n + 1] << np.uint64(24)) | (padded[2:n + 2] << np.uint64(16)) | \
+              (padded[3:n + 3] << np.uint64(8)) | padded[4:n + 4]
+        win = np.empty((n, 8), dtype=np.uint32)
+        for sh in range(8):
+            win[:, sh] = ((w40 >> np.uint64(8 - sh)) & np.uint64(0xFFFFFFFF)).astype(np.uint32)
         self.win = win.reshape(-1)
+        nb = n * 8
         bits = np.unpackbits(raw)
-        idx = np.where(bits == 1, np.arange(self.nbits, dtype=np.int64), np.int64(self.nbits))
-        self.next_one = np.minimum.accumulate(idx[::-1])[::-1]
-        self.pos = 0
+        idx = np.where(bits == 1, np.arange(nb, dtype=np.int32), np.int32(nb))
+        self.next_one = np.minimum.accumulate(idx[::-1])[::-1] if nb else idx
+        self.base = byte0 * 8
+        self.wbits = nb
+        # reads near the end of the window are only safe when the window ends with the data
+        self.limit = nb if byte0 + n >= len(self.data) else nb - 64
+
+    def ensure(self, need_bits):
+        """Make the window cover ``need_bits`` bits from the cursor (a whole frame) without another reload."""
+        rel = self.pos - self.base
+        if rel + need_bits > self.limit and self.base + self.wbits < self.nbits:
+            self._load(self.pos // 8, max(self.WINDOW, (need_bits + 7) // 8 + 64))
+
+    def _rel(self, k):
+        rel = self.pos - self.base
+        if rel + k > self.limit and self.base + self.wbits < self.nbits:
+            self._load(self.pos // 8, self.WINDOW)
+            rel = self.pos - self.base
+        return rel
 
     def u(self, k):
         """Unsigned k-bit field (k <= 32) at the cursor."""
         if k == 0:
             return 0
-        v = int(self.win[self.pos]) >> (32 - k)
+        v = int(self.win[self._rel(k)]) >> (32 - k)
         self.pos += k
         return v
 
@@ -81,9 +112,12 @@ class _Bits:
         return v - (1 << k) if k and v >> (k - 1) else v
 
     def unary(self):
-        p = int(self.next_one[self.pos])
-        q = p - self.pos
-        self.pos = p + 1
+        rel = self._rel(64)
+        p = int(self.next_one[rel])
+        if p >= self.wbits and self.base + self.wbits < self.nbits:
+            raise ValueError("FLAC: unary code longer than the decoder's window")
+        q = p - rel
+        self.pos += q + 1
         return q
 
 
@@ -95,7 +129,6 @@ def _residual(br, blocksize, order, out):
     esc = (1 << pbits) - 1
     porder = br.u(4)
     nparts = 1 << porder
-    win, next_one = br.win, br.next_one
     i = order
     for part in range(nparts):
         count = (blocksize >> porder) - (order if part == 0 else 0)
@@ -106,7 +139,9 @@ def _residual(br, blocksize, order, out):
                 out[i] = br.s(raw_bits) if raw_bits else 0
                 i += 1
             continue
-        pos = br.pos
+        # the caller's ensure() put the whole frame inside the window: window-relative positions from here on
+        win, next_one, top = br.win, br.next_one, br.wbits
+        pos = br.pos - br.base
         shift = 32 - k
         if k:
             for _ in range(count):
@@ -122,7 +157,9 @@ def _residual(br, blocksize, order, out):
                 pos = p + 1
                 out[i] = (u >> 1) ^ -(u & 1)
                 i += 1
-        br.pos = pos
+        if pos > top:
+            raise ValueError("FLAC: residual runs past the decoder's window (corrupt stream?)")
+        br.pos = br.base + pos
 
 
 def _predict(out, order, coeffs, shift):
@@ -245,6 +282,7 @@ def decode_flac(data, verify_md5=False):
             br.u(16)
         br.u(8)                                   # CRC-8 of the header
         bps = _SAMPLE_SIZES.get(ss_code, bps_stream)
+        br.ensure(blocksize * (ch_assign + 1 if ch_assign < 8 else 2) * 64 + 4096)     # the whole frame inside the window
         if ch_assign < 8:
             subs = [_subframe(br, blocksize, bps) for _ in range(ch_assign + 1)]
         elif ch_assign == 8:                      # left / side
