@@ -122,8 +122,7 @@ struct IstftFusedCfg {
 	using S = FftSched<LOG2M>;
 	static constexpr int BLOCK = S::TPF < 128 ? 128 : S::TPF;
 	static constexpr int SLOTS = BLOCK / S::TPF;
-	static constexpr int STAGE_F2 = (S::M + 2) & ~1;                    // one-sided spectrum of the NEXT frame (M + 1 bins)
-	static constexpr int SLOT_FLOATS = 2 * S::BUF + 2 * S::M + 2 * STAGE_F2;   // FFT buffer + circular overlap-add buffer + stage
+	static constexpr int SLOT_FLOATS = 2 * S::BUF + 2 * S::M;          // FFT buffer + circular overlap-add buffer
 	static constexpr int SMEM = SLOTS * SLOT_FLOATS * (int)sizeof(float);
 };
 
@@ -138,15 +137,7 @@ istft_fused_kernel(IstftArgs a, const float2 *__restrict__ tw, float scale, int6
 	const int tid = threadIdx.x % S::TPF;
 	float2 *buf = reinterpret_cast<float2 *>(smem_f + slot * C::SLOT_FLOATS);
 	float *ola = smem_f + slot * C::SLOT_FLOATS + 2 * S::BUF;
-	float2 *stage = reinterpret_cast<float2 *>(ola + 2 * S::M);
 	const SlotSync<S::TPF> sync{slot + 1};
-	// the one-sided spectrum of a frame -> stage, asynchronously (8-byte cp.async; rows are only 8-byte aligned)
-	auto prefetch_row = [&](int64_t ch, int64_t t) {
-		const float2 *row = a.S + ch * a.s_ch_stride + t * a.s_pitch;
-		for (int k = tid; k <= S::M; k += S::TPF)
-			asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(stage + k)), "l"(row + k) : "memory");
-		asm volatile("cp.async.commit_group;" ::: "memory");
-	};
 	const float2 *tws = tw + S::TW_SPLIT_OFFSET;
 	const float2 *win2 = reinterpret_cast<const float2 *>(a.window);
 	const int64_t total = (int64_t)a.n_ch * runs_per_ch;
@@ -160,13 +151,11 @@ istft_fused_kernel(IstftArgs a, const float2 *__restrict__ tw, float scale, int6
 		const int64_t first = own0 - (ov - 1) > 0 ? own0 - (ov - 1) : 0;
 		for (int r = tid; r < N; r += S::TPF) ola[r] = 0.f;
 		float *ych = a.y + ch * a.y_ch_stride;
-		prefetch_row(ch, first);
 		for (int64_t t = first; t < own1; t++) {
-			asm volatile("cp.async.wait_group 0;" ::: "memory");
-			sync();                               // every thread's part of the row has landed
 			// fold the one-sided spectrum into the M-point complex spectrum of z[n] = x[2n] + i x[2n+1]
+			const float2 *row = a.S + ch * a.s_ch_stride + t * a.s_pitch;
 			for (int k = tid; k <= S::M / 2; k += S::TPF) {
-				float2 xk = stage[k], xm = stage[S::M - k];
+				float2 xk = __ldg(row + k), xm = __ldg(row + S::M - k);
 				if (k == 0) {   // irfft ignores the imaginary parts of the DC and Nyquist bins
 					xk.y = 0.f;
 					xm.y = 0.f;
@@ -178,8 +167,6 @@ istft_fused_kernel(IstftArgs a, const float2 *__restrict__ tw, float scale, int6
 				buf[pad16(k)] = make_float2(e.x - o.y, e.y + o.x);
 				if (k != 0 && k != S::M - k) buf[pad16(S::M - k)] = make_float2(e.x + o.y, o.x - e.y);
 			}
-			sync();                               // the stage has been consumed: fetch the next frame behind this one's work
-			if (t + 1 < own1) prefetch_row(ch, t + 1);
 			RunPassesSlot<LOG2M, true, 0, SlotSync<S::TPF>>::run(tid, buf, tw, sync);
 			sync();
 			// overlap-add: sample r of frame t lands in slot (t*hop + r) mod N
@@ -297,17 +284,18 @@ static bool istft_two_pass_forced() {
 }
 
 // does launch_istft need IstftArgs::frames (n_ch * n_frames * n_fft floats of scratch)?
-bool istft_needs_scratch(int n_fft) { return istft_two_pass_forced() || n_fft > 16384; }
+bool istft_needs_scratch(int n_fft) { return istft_two_pass_forced() || n_fft > 8192; }
 
 int launch_istft(const IstftArgs &a, int device, cudaStream_t st) {
 	int log2m = -1;
 	for (int b = 4; b <= 14; b++)
 		if (a.n_fft == (2 << b)) log2m = b;
 	int rc;
-	// fused inverse transform + overlap-add (no scratch) up to 16384 points; $PAR_B200_ISTFT_TWO_PASS=1 selects the
+	// fused inverse transform + overlap-add (no scratch) up to 8192 points (above, a slot's serial frame chain is slower
+	// than the two-pass pair: measured 3.0 vs 2.6 ms at 16384); $PAR_B200_ISTFT_TWO_PASS=1 selects the
 	// frames-to-scratch + gather pair for every size (tests compare the two: identical bits)
 	const bool two_pass = istft_two_pass_forced();
-	if (!two_pass && log2m >= 4 && log2m <= 13 && a.n_frames > 0 && a.length > 0) {
+	if (!two_pass && log2m >= 4 && log2m <= 12 && a.n_frames > 0 && a.length > 0) {
 		switch (log2m) {
 		case 4: return launch_fused<4>(a, device, st);
 		case 5: return launch_fused<5>(a, device, st);
@@ -318,7 +306,6 @@ int launch_istft(const IstftArgs &a, int device, cudaStream_t st) {
 		case 10: return launch_fused<10>(a, device, st);
 		case 11: return launch_fused<11>(a, device, st);
 		case 12: return launch_fused<12>(a, device, st);
-		case 13: return launch_fused<13>(a, device, st);
 		}
 	}
 	if (!a.frames) { set_error("istft: internal error (no scratch for the two-pass path)"); return PAR_EINVAL; }

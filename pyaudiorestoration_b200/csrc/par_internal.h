@@ -62,7 +62,7 @@ struct IstftArgs {
 	float *frames;         // device scratch: n_ch * n_frames * n_fft floats
 };
 int launch_istft(const IstftArgs &a, int device, cudaStream_t st);
-bool istft_needs_scratch(int n_fft);      // only the two-pass path (n_fft 32768) uses IstftArgs::frames
+bool istft_needs_scratch(int n_fft);      // only the two-pass path (n_fft > 8192) uses IstftArgs::frames
 
 // STFT-domain mask operators (spectral.cu); S is a device spectrogram, frames `pitch` float2 apart, bins contiguous
 int launch_spec_gate(float2 *S, int64_t cells, int F, const double *thr_db_dev, double gain_db, int device, cudaStream_t st);
