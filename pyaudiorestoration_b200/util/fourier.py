@@ -140,6 +140,10 @@ def stft(x, n_fft=1024, step=512, window_name='blackmanharris', zeropad=1):
 
     x : 1-D real array-like (any stride / real dtype).  Returns ndarray (n_freqs, n_steps)
     complex64, ``n_freqs = n_fft*zeropad//2 + 1``, ``n_steps = len(x)//step + 1``.
+
+    Size restriction (the reference accepts any ``n_fft``): ``n_fft * zeropad`` must be a power of two in
+    [32, 1048576] -- every size the reference's GUIs offer (util/widgets.py:333-335); anything else raises
+    ``RuntimeError`` (``PAR_EUNSUPPORTED``), there is no CPU fallback.
     """
     with timed_log("b200"):
         return _stft_call(x, n_fft, step, window_name, zeropad, False)
@@ -210,6 +214,7 @@ def istft(stft_matrix, hop_length=None, win_length=None, window_name='blackmanha
 
     The arithmetic is float32 on the device for every input dtype; a complex128 argument still
     yields a float64 array like the reference, but carries float32 accuracy.
+    Size restriction: ``n_fft = 2 * (n_freqs - 1)`` must be a power of two in [32, 32768] (``RuntimeError`` otherwise).
     """
     stft_matrix = np.asarray(stft_matrix)
     if stft_matrix.ndim != 2:
