@@ -572,6 +572,290 @@ sinc_kernel(const __grid_constant__ SincArgs a, const __grid_constant__ SincTab<
 	}
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Warp-specialised variant: one CTA per SM, WS_CWARPS interpolating warps + WS_PWARPS set-up warps.
+// The set-up warps run stages A and B of tile w + 1 (positions -> records, span, unit table, cp.async of
+// the span) while the interpolating warps run stage C/D of tile w; the two sides meet only at four
+// named barriers (full / empty per buffer).  Same records, same units, same sinc_unit arithmetic as
+// sinc_kernel: the outputs are bit-identical, only who computes the records differs.
+// ------------------------------------------------------------------------------------------
+#ifndef SINC_WS_CWARPS
+#define SINC_WS_CWARPS 14
+#endif
+#ifndef SINC_WS_PWARPS
+#define SINC_WS_PWARPS 2
+#endif
+#ifndef SINC_WS_UNROLL
+#define SINC_WS_UNROLL 2
+#endif
+constexpr int WS_CT = 32 * SINC_WS_CWARPS, WS_PT = 32 * SINC_WS_PWARPS, WS_THREADS = WS_CT + WS_PT;
+constexpr int WS_TILE = 2 * WS_CT - 16;
+constexpr int WS_PER = (WS_TILE + WS_PT - 1) / WS_PT;       // outputs per set-up thread
+constexpr int kWsUnroll = SINC_WS_UNROLL;
+constexpr int WS_BAR_FULL = 1, WS_BAR_EMPTY = 3, WS_BAR_PROD = 5;   // named barriers (0 is __syncthreads)
+
+__device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// One word per output: flags in bits 0..2, (tap-run start relative to the tile's reference sample + WS_BIAS) above.
+constexpr int WS_BIAS = 1 << 27;
+struct WsTileBuf {
+	unsigned long long g[WS_TILE + 2];     // entry WS_TILE of g, sfx, s, fc: stand-in for the empty half of a unit
+	long long sfx[WS_TILE + 2];
+	float s[WS_TILE + 2];
+	float fc[WS_TILE + 2];
+	unsigned rec[WS_TILE + 2];      // entries WS_TILE, WS_TILE + 1 stay 0 (not fast)
+	int unit[WS_TILE];              // first output of the unit | paired << 16
+	long long i0;
+	int n_units, ch0, adj, staged;  // centre index in the staged span = (rec >> 3) + adj
+};
+struct WsSmem {
+	WsTileBuf tb[2];
+	double pos[2][WS_TILE + 2];
+	int red[2][SINC_WS_PWARPS];
+	int wsum[SINC_WS_PWARPS];
+};
+
+template <int CH, int CAP>
+__global__ void __launch_bounds__(WS_THREADS, 1)
+sinc_kernel_ws(const __grid_constant__ SincArgs a, const __grid_constant__ SincTab<CAP> tab,
+               const float *__restrict__ ctab, const float *__restrict__ hptab, const int span_cap) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	WsSmem &sm = *reinterpret_cast<WsSmem *>(smem_raw);
+	float *xs_all = reinterpret_cast<float *>(smem_raw + ((sizeof(WsSmem) + 15) & ~(size_t)15));
+	const int xpitch = SINC_XFRONT + span_cap + SINC_XPAD;
+	const int nt = a.nt;
+	const int tid = threadIdx.x;
+	const int64_t tiles = (a.out_end - a.out_begin + WS_TILE - 1) / WS_TILE;
+	const int groups = (a.n_ch + CH - 1) / CH;
+	const int64_t work = tiles * groups;
+	const int64_t per_cta = (work + gridDim.x - 1) / gridDim.x;
+	const int64_t w0 = (int64_t)blockIdx.x * per_cta;
+	const int64_t w1 = w0 + per_cta < work ? w0 + per_cta : work;
+	if (w0 >= w1) return;
+	const double *posg = a.pos - a.pos_origin;
+	for (int e = tid; e < 2 * CH * SINC_XFRONT; e += WS_THREADS) {
+		const int bufi = e / (CH * SINC_XFRONT), r = e % (CH * SINC_XFRONT), par = r / (CH * SINC_XFRONT / 2), q = r % (CH * SINC_XFRONT / 2);
+		xs_all[bufi * CH * xpitch + par * (xpitch / 2) * CH + q] = 0.f;
+	}
+	if (tid < 4) {
+		WsTileBuf &t = sm.tb[tid >> 1];
+		const int e = WS_TILE + (tid & 1);
+		t.rec[e] = 0u; t.s[e] = 0.5f; t.fc[e] = 1.f; t.g[e] = 0; t.sfx[e] = 0;
+	}
+	__syncthreads();
+	int grp = (int)(w0 / tiles);
+	int64_t tile = w0 - (int64_t)grp * tiles;
+
+	if (tid >= WS_CT) {
+		// =============================== set-up warps ===============================
+#ifdef SINC_WS_REGS_P
+		asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SINC_WS_REGS_P));
+#endif
+		const int pt = tid - WS_CT, lane = pt & 31, pw = pt >> 5;
+		auto prefetch_pos = [&](int64_t tl, int pb) {
+			const int64_t i0 = a.out_begin + tl * WS_TILE;
+			int64_t cnt = a.m - i0;
+			if (cnt > WS_TILE + 1) cnt = WS_TILE + 1;
+			for (int e = pt; e < cnt; e += WS_PT) cp_async8(&sm.pos[pb][e], posg + i0 + e);
+		};
+		prefetch_pos(tile, 0);
+		cp_async_commit();
+		// read period of the last output (the reference repeats the previous one)
+		const double per_tail = a.m >= 2 ? fmax(1e-12, posg[a.m - 1] - posg[a.m - 2]) : 0.0;
+		const bool aligned = a.aligned_edges != 0;
+		for (int64_t w = w0; w < w1; w++) {
+			const int buf = (int)((w - w0) & 1);
+			WsTileBuf &tb = sm.tb[buf];
+			const double *tpos = sm.pos[buf];
+			int grp_n = grp;
+			int64_t tile_n = tile;
+			if (++tile_n == tiles) { tile_n = 0; grp_n++; }
+			cp_async_wait_all();                                   // positions of this tile (issued a tile ago)
+			named_sync(WS_BAR_PROD, WS_PT);
+			if (w + 1 < w1) prefetch_pos(tile_n, buf ^ 1);         // pos[buf ^ 1] was last read two barriers ago
+			cp_async_commit();
+			if (w >= w0 + 2) named_sync(WS_BAR_EMPTY + buf, WS_THREADS);   // tile w - 2 has left this buffer
+			const int64_t i0 = a.out_begin + tile * WS_TILE;
+			double rf = rint(tpos[0]);
+			if (!(rf > -9.0e15)) rf = -9.0e15;
+			if (rf > 9.0e15) rf = 9.0e15;
+			const long long ref = (long long)rf - nt;
+			int lo_min = INT_MAX, hi_max = INT_MIN;
+			// pass 1: the float64 set-up of every output, straight-line so that the unrolled iterations interleave
+			// (outputs behind the end of the range are set up from whatever the buffer holds and marked dead)
+#pragma unroll kWsUnroll
+			for (int o = pt; o < WS_TILE; o += WS_PT) {
+				const int64_t i = i0 + o;
+				const double p = tpos[o];
+				const double per = i + 1 < a.m ? fmax(1e-12, tpos[o + 1] - p) : per_tail;
+				const SincSetup su = sinc_setup(p, per, nt, a.n_in, aligned);
+				const bool live = i < a.out_end;
+				const bool fast = live && su.cnt == 2 * nt && su.koff == 0;
+				long long rel = su.lower - ref;
+				rel = rel < -(1ll << 26) ? -(1ll << 26) : (rel > (1ll << 26) ? (1ll << 26) : rel);
+				const int rel32 = (int)rel;
+				lo_min = fast ? min(lo_min, rel32) : lo_min;
+				hi_max = fast ? max(hi_max, rel32 + 2 * nt) : hi_max;
+				tb.s[o] = su.slot.s;
+				tb.fc[o] = su.slot.fc;
+				tb.g[o] = su.slot.g_fx;
+				tb.sfx[o] = su.slot.s_fx;
+				tb.rec[o] = (live ? SO_LIVE : 0u) | (live && su.lowpass ? SO_LOWPASS : 0u) |
+				            (fast ? SO_FAST | ((unsigned)(rel32 + WS_BIAS) << 3) : 0u);
+			}
+			lo_min = __reduce_min_sync(0xffffffffu, lo_min);
+			hi_max = __reduce_max_sync(0xffffffffu, hi_max);
+			if (lane == 0) { sm.red[0][pw] = lo_min; sm.red[1][pw] = hi_max; }
+			named_sync(WS_BAR_PROD, WS_PT);
+#pragma unroll
+			for (int wv = 0; wv < SINC_WS_PWARPS; wv++) { lo_min = min(lo_min, sm.red[0][wv]); hi_max = max(hi_max, sm.red[1][wv]); }
+			const long long tlo = (ref + lo_min) & ~3ll;
+			const bool any = hi_max > lo_min;
+			const int span = any ? (int)(ref + hi_max - tlo) : 0;
+			const bool staged = any && lo_min > -(1 << 26) && hi_max < (1 << 26) && span <= span_cap;
+			// the span's copies go out first: they fly while the units are formed
+			if (staged) {
+				float *xs = xs_all + buf * CH * xpitch;
+				const int plane = (xpitch / 2) * CH;
+				const int len = span + SINC_XPAD;
+#pragma unroll
+				for (int c = 0; c < CH; c++) {
+					const bool have = grp * CH + c < a.n_ch;
+					const float *src = a.signal + (int64_t)(grp * CH + c) * a.sig_ch_stride + (tlo - a.sig_origin) * a.sig_stride;
+					float *d0 = xs + ((SINC_XFRONT >> 1) + pt) * CH + c, *d1 = d0 + plane;
+					const int sp_n = have ? span : 0;
+					if (a.sig_stride == 1) {
+						const float *sp = src + 2 * pt;
+						for (int e = 2 * pt; e < len; e += 2 * WS_PT, sp += 2 * WS_PT, d0 += WS_PT * CH, d1 += WS_PT * CH) {
+							if (e < sp_n) cp_async4(d0, sp); else *d0 = 0.f;
+							if (e + 1 < sp_n) cp_async4(d1, sp + 1); else *d1 = 0.f;
+						}
+					} else {
+						for (int e = 2 * pt; e < len; e += 2 * WS_PT, d0 += WS_PT * CH, d1 += WS_PT * CH) {
+							if (e < sp_n) cp_async4(d0, src + (int64_t)e * a.sig_stride); else *d0 = 0.f;
+							if (e + 1 < sp_n) cp_async4(d1, src + (int64_t)(e + 1) * a.sig_stride); else *d1 = 0.f;
+						}
+					}
+				}
+			}
+			cp_async_commit();
+			// pass 2: units over this thread's run of consecutive outputs; the centre index of an output in
+			// the staged span is (rec >> 3) + adj, so its parity is that of (rec >> 3) + adj
+			const int adj = (int)(ref - tlo) + nt - WS_BIAS;
+			const int c0 = pt * WS_PER;
+			unsigned wd[WS_PER + 2];
+#pragma unroll
+			for (int j = 0; j < WS_PER + 2; j++) {
+				const int o = c0 - 1 + j;
+				wd[j] = (o >= 0 && o <= WS_TILE) ? tb.rec[o] : 0u;
+			}
+			unsigned starts = 0u, heads = 0u;
+			if (staged) {
+				bool hprev;
+				{
+					const unsigned k0 = wd[0] >> 3, k1 = wd[1] >> 3;
+					hprev = (wd[0] & wd[1] & SO_FAST) && !((k0 + (unsigned)adj) & 1u) && k1 == k0 + 1 && !((wd[0] ^ wd[1]) & SO_LOWPASS);
+				}
+#pragma unroll
+				for (int j = 1; j <= WS_PER; j++) {
+					const unsigned k0 = wd[j] >> 3, k1 = wd[j + 1] >> 3;
+					const bool h = (wd[j] & wd[j + 1] & SO_FAST) && !((k0 + (unsigned)adj) & 1u) && k1 == k0 + 1 &&
+					               !((wd[j] ^ wd[j + 1]) & SO_LOWPASS);
+					if (c0 + j - 1 < WS_TILE) {
+						if ((wd[j] & SO_FAST) && !hprev) starts |= 1u << (j - 1);
+						if (h) heads |= 1u << (j - 1);
+					}
+					hprev = h;
+				}
+			}
+			const int cnt = __popc(starts);
+			int inc = cnt;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const int v = __shfl_up_sync(0xffffffffu, inc, d);
+				if (lane >= d) inc += v;
+			}
+			if (lane == 31) sm.wsum[pw] = inc;
+			named_sync(WS_BAR_PROD, WS_PT);
+			int base = 0, total = 0;
+#pragma unroll
+			for (int wv = 0; wv < SINC_WS_PWARPS; wv++) {
+				if (wv < pw) base += sm.wsum[wv];
+				total += sm.wsum[wv];
+			}
+			int idx = base + inc - cnt;
+			while (starts) {
+				const int j = __ffs(starts) - 1;
+				starts &= starts - 1;
+				tb.unit[idx++] = (c0 + j) | (((heads >> j) & 1u) ? 0x10000 : 0);
+			}
+			if (pt == 0) { tb.i0 = i0; tb.n_units = total; tb.ch0 = grp * CH; tb.adj = adj; tb.staged = staged ? 1 : 0; }
+			cp_async_wait_all();                                    // the span (and the next positions) have landed
+			__threadfence_block();
+			named_arrive(WS_BAR_FULL + buf, WS_THREADS);
+			grp = grp_n; tile = tile_n;
+		}
+		return;
+	}
+
+	// =============================== interpolating warps ===============================
+#ifdef SINC_WS_REGS_C
+	asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SINC_WS_REGS_C));
+#endif
+	for (int64_t w = w0; w < w1; w++) {
+		const int buf = (int)((w - w0) & 1);
+		named_sync(WS_BAR_FULL + buf, WS_THREADS);
+		const WsTileBuf &tb = sm.tb[buf];
+		const float *xs = xs_all + buf * CH * xpitch;
+		const int64_t i0 = tb.i0;
+		const int n_units = tb.n_units, ch0 = tb.ch0, adj = tb.adj;
+		const bool staged = tb.staged != 0;
+		for (int u = tid; u < n_units; u += WS_CT) {
+			const int code = tb.unit[u];
+			const int o = code & 0xffff;
+			const bool paired = (code >> 16) != 0;
+			const unsigned word = tb.rec[o];
+			const int lo0 = (int)(word >> 3) + adj;
+			const int oE = (paired || !(lo0 & 1)) ? o : -1;
+			const int oO = paired ? o + 1 : ((lo0 & 1) ? o : -1);
+			const int j0 = lo0 & ~1;
+			const bool lowpass = (word & SO_LOWPASS) != 0;
+			const int iE = oE >= 0 ? oE : WS_TILE, iO = oO >= 0 ? oO : WS_TILE;
+			const SincSlotRef sl[2] = {{&tb.s[iE], &tb.fc[iE], &tb.g[iE], &tb.sfx[iE]}, {&tb.s[iO], &tb.fc[iO], &tb.g[iO], &tb.sfx[iO]}};
+			float y[2][CH];
+			const SincWin<CH> xu{xs + ((SINC_XFRONT + j0) >> 1) * CH, (xpitch / 2) * CH};
+			if (lowpass) sinc_unit<CH, true, 2, CAP>(nt, tab, xu, sl, y);
+			else sinc_unit<CH, false, 2, CAP>(nt, tab, xu, sl, y);
+#pragma unroll
+			for (int c = 0; c < CH; c++) {
+				if (ch0 + c < a.n_ch) {
+					float *dst = a.out + (int64_t)(ch0 + c) * a.out_ch_stride - a.out_origin * a.out_stride;
+					if (oE >= 0) dst[(i0 + oE) * a.out_stride] = y[0][c];
+					if (oO >= 0) dst[(i0 + oO) * a.out_stride] = y[1][c];
+				}
+			}
+		}
+		for (int o = tid; o < WS_TILE; o += WS_CT) {
+			const unsigned fl = tb.rec[o];
+			if ((fl & SO_LIVE) && !((fl & SO_FAST) && staged)) {
+				const int64_t i = i0 + o;
+				const SincSetup su = sinc_setup_at(a, i);
+				for (int c = 0; c < CH; c++) {
+					if (ch0 + c >= a.n_ch) break;
+					float y = 0.f;
+					if (su.cnt > 0)
+						y = taps_slow(su, nt, ctab, hptab,
+						              a.signal + (int64_t)(ch0 + c) * a.sig_ch_stride - a.sig_origin * a.sig_stride, a.sig_stride);
+					a.out[(int64_t)(ch0 + c) * a.out_ch_stride + (i - a.out_origin) * a.out_stride] = y;
+				}
+			}
+		}
+		if (w + 2 < w1) named_arrive(WS_BAR_EMPTY + buf, WS_THREADS);
+	}
+}
+
 // distance table of sinc_core.cuh per NT (host cache, passed to the kernel by value)
 template <int CAP>
 static const SincTab<CAP> *sinc_param_table(int nt) {
@@ -587,8 +871,33 @@ static const SincTab<CAP> *sinc_param_table(int nt) {
 	return it->second.get();
 }
 
+static bool sinc_use_ws() {
+	static const bool on = [] { const char *e = getenv("PAR_B200_SINC_WS"); return e && e[0] == '1'; }();
+	return on;
+}
+
+template <int CH, int CAP>
+static int launch_sinc_ws(const SincArgs &a, int device, cudaStream_t st, const SincTables &tb) {
+	int span_cap = 2 * WS_TILE + 2 * a.nt + 8;
+	span_cap = (span_cap + 3) & ~3;
+	const int smem = (int)((sizeof(WsSmem) + 15) & ~(size_t)15) + 2 * CH * (SINC_XFRONT + span_cap + SINC_XPAD) * (int)sizeof(float);
+	auto kern = sinc_kernel_ws<CH, CAP>;
+	PAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+	const int64_t tiles = (a.out_end - a.out_begin + WS_TILE - 1) / WS_TILE;
+	const int64_t work = tiles * ((a.n_ch + CH - 1) / CH);
+	int64_t grid = sm_count(device);
+	if (grid > work) grid = work;
+	if (grid < 1) return PAR_OK;
+	const SincTab<CAP> *pt = sinc_param_table<CAP>(a.nt);
+	kern<<<(unsigned)grid, WS_THREADS, smem, st>>>(a, *pt, tb.c, tb.hp, span_cap);
+	count_launch();
+	PAR_CUDA(cudaGetLastError());
+	return PAR_OK;
+}
+
 template <int CH, int CAP>
 static int launch_sinc_ch(const SincArgs &a, int device, cudaStream_t st, const SincTables &tb) {
+	if (sinc_use_ws()) return launch_sinc_ws<CH, CAP>(a, device, st, tb);
 	// widest span staged in shared memory: a tile read at up to ~2.5x speed
 	int span_cap = 2 * SINC_TILE + 2 * a.nt + 8;
 	span_cap = (span_cap + 3) & ~3;

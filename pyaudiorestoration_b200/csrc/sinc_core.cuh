@@ -388,48 +388,67 @@ struct SincSetup {
 	uint64_t f_fx;     // fc in units of 2^-63 half-turns (edge path)
 };
 
-SC_HD SincSetup sinc_setup(double p, double per, int nt, int64_t n_in, bool aligned_edges) {
-	SincSetup su;
-	// fc = min(1 / per, 1): a single-precision reciprocal refined by two Newton steps in float64 (relative error
-	// < 1e-15: fc only enters the weights through pi * (1 - fc) * d, d < 512) instead of the IEEE division sequence
-	double fc = 1.0;
-	if (per > 1.0) {
-		const double r0 = (double)sc_rcp((float)per);
-		const double r1 = fma(fma(-per, r0, 1.0), r0, r0);
-		fc = fma(fma(-per, r1, 1.0), r1, r1);
-		if (!(fc < 1.0)) fc = 1.0;
-	}
+// fc = min(1 / per, 1): a single-precision reciprocal refined by two Newton steps in float64 (relative error
+// < 1e-15: fc only enters the weights through pi * (1 - fc) * d, d < 512) instead of the IEEE division sequence
+SC_HD double sinc_fc(double per) {
+	// straight-line on purpose (several outputs are set up interleaved): the Newton value is dropped for per <= 1
+	const double pc = per > 1.0 ? per : 2.0;
+	const double r0 = (double)sc_rcp((float)pc);
+	const double r1 = fma(fma(-pc, r0, 1.0), r0, r0);
+	const double r2 = fma(fma(-pc, r1, 1.0), r1, r1);
+	return (per > 1.0 && r2 < 1.0) ? r2 : 1.0;
+}
+
+// Index part of the set-up: which taps an output reads and whether it is low-passed.
+struct SincIndex {
+	int64_t lower;
+	int cnt, koff;
+	bool lowpass;
+};
+SC_HD SincIndex sinc_index(double p, double per, int nt, int64_t n_in, bool aligned_edges, double *fc_out = nullptr,
+                           double *pr_out = nullptr) {
+	SincIndex ix;
+	const double fc = sinc_fc(per);
 	double pr = rint(p);                        // half to even, like Python's round()
 	if (!(pr > -9.0e15)) pr = -9.0e15;          // NaN / -inf guard (garbage in, zeros out)
 	if (pr > 9.0e15) pr = 9.0e15;
 	const long long ind = (long long)pr;
-	const double sd = p - pr;
 	long long lower = ind - nt, upper = ind + nt;
 	if (lower < 0) lower = 0;
 	if (upper > n_in) upper = n_in;
-	su.lower = lower;
-	su.cnt = upper > lower ? (int)(upper - lower) : 0;
-	su.koff = aligned_edges ? (int)(lower - (ind - nt)) : 0;
+	ix.lower = lower;
+	ix.cnt = upper > lower ? (int)(upper - lower) : 0;
+	ix.koff = aligned_edges ? (int)(lower - (ind - nt)) : 0;
+	ix.lowpass = fc < 1.0;
+	if (fc_out) *fc_out = fc;
+	if (pr_out) *pr_out = pr;
+	return ix;
+}
+
+SC_HD SincSetup sinc_setup(double p, double per, int nt, int64_t n_in, bool aligned_edges) {
+	SincSetup su;
+	double fc, pr;
+	const SincIndex ix = sinc_index(p, per, nt, n_in, aligned_edges, &fc, &pr);
+	const double sd = p - pr;
+	su.lower = ix.lower;
+	su.cnt = ix.cnt;
+	su.koff = ix.koff;
 	float s = (float)sd;
 	if (s == 0.f) s = 1e-30f;
 	su.slot.s = s;
-	su.lowpass = fc < 1.0;
+	su.lowpass = ix.lowpass;
 	su.slot.fc = (float)fc;
-	su.slot.g_fx = 0;
-	su.slot.s_fx = 0;
-	su.f_fx = 0;
-	if (su.lowpass) {
-		// fc in (0, 1): fc * 2^63 < 2^63; g = 1 - fc is exact in float64 for fc >= 0.5
-		const double f63 = fc * 9223372036854775808.0;
+	// fc in (0, 1): fc * 2^63 < 2^63; g = 1 - fc is exact in float64 for fc >= 0.5.  Straight-line: fc = 1 converts 0.
+	const double f63 = su.lowpass ? fc * 9223372036854775808.0 : 0.0;
+	const double s63 = su.lowpass ? fc * sd * 9223372036854775808.0 : 0.0;
 #if defined(__CUDA_ARCH__)
-		su.f_fx = __double2ull_rn(f63);
-		su.slot.s_fx = __double2ll_rn(fc * sd * 9223372036854775808.0);
+	su.f_fx = __double2ull_rn(f63);
+	su.slot.s_fx = __double2ll_rn(s63);
 #else
-		su.f_fx = (uint64_t)llrint(f63);
-		su.slot.s_fx = (int64_t)llrint(fc * sd * 9223372036854775808.0);
+	su.f_fx = (uint64_t)llrint(f63);
+	su.slot.s_fx = (int64_t)llrint(s63);
 #endif
-		su.slot.g_fx = 9223372036854775808ull - su.f_fx;
-	}
+	su.slot.g_fx = su.lowpass ? 9223372036854775808ull - su.f_fx : 0ull;
 	return su;
 }
 
