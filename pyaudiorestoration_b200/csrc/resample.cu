@@ -581,13 +581,13 @@ sinc_kernel(const __grid_constant__ SincArgs a, const __grid_constant__ SincTab<
 // sinc_kernel: the outputs are bit-identical, only who computes the records differs.
 // ------------------------------------------------------------------------------------------
 #ifndef SINC_WS_CWARPS
-#define SINC_WS_CWARPS 14
+#define SINC_WS_CWARPS 12
 #endif
 #ifndef SINC_WS_PWARPS
-#define SINC_WS_PWARPS 2
+#define SINC_WS_PWARPS 4
 #endif
 #ifndef SINC_WS_UNROLL
-#define SINC_WS_UNROLL 2
+#define SINC_WS_UNROLL 4
 #endif
 constexpr int WS_CT = 32 * SINC_WS_CWARPS, WS_PT = 32 * SINC_WS_PWARPS, WS_THREADS = WS_CT + WS_PT;
 constexpr int WS_TILE = 2 * WS_CT - 16;
@@ -871,14 +871,18 @@ static const SincTab<CAP> *sinc_param_table(int nt) {
 	return it->second.get();
 }
 
-static bool sinc_use_ws() {
-	static const bool on = [] { const char *e = getenv("PAR_B200_SINC_WS"); return e && e[0] == '1'; }();
-	return on;
+// Which kernel: the warp-specialised one from 64 taps up (measured on B200: 100 taps 3.32 vs 3.75 ms, 256 taps 5.94 vs
+// 6.56 ms; 16 taps 0.27 vs 0.20 ms -- with few taps the set-up warps cannot keep up).  PAR_B200_SINC_WS=0/1 forces one.
+static bool sinc_use_ws(int nt) {
+	static const int forced = [] { const char *e = getenv("PAR_B200_SINC_WS"); return e && (e[0] == '0' || e[0] == '1') ? e[0] - '0' : -1; }();
+	if (forced >= 0) return forced == 1;
+	return nt >= 32;
 }
 
 template <int CH, int CAP>
 static int launch_sinc_ws(const SincArgs &a, int device, cudaStream_t st, const SincTables &tb) {
-	int span_cap = 2 * WS_TILE + 2 * a.nt + 8;
+	// widest span staged in shared memory: a tile read at up to ~4x speed (one CTA per SM: room for it)
+	int span_cap = 4 * WS_TILE + 2 * a.nt + 8;
 	span_cap = (span_cap + 3) & ~3;
 	const int smem = (int)((sizeof(WsSmem) + 15) & ~(size_t)15) + 2 * CH * (SINC_XFRONT + span_cap + SINC_XPAD) * (int)sizeof(float);
 	auto kern = sinc_kernel_ws<CH, CAP>;
@@ -897,7 +901,7 @@ static int launch_sinc_ws(const SincArgs &a, int device, cudaStream_t st, const 
 
 template <int CH, int CAP>
 static int launch_sinc_ch(const SincArgs &a, int device, cudaStream_t st, const SincTables &tb) {
-	if (sinc_use_ws()) return launch_sinc_ws<CH, CAP>(a, device, st, tb);
+	if (sinc_use_ws(a.nt)) return launch_sinc_ws<CH, CAP>(a, device, st, tb);
 	// widest span staged in shared memory: a tile read at up to ~2.5x speed
 	int span_cap = 2 * SINC_TILE + 2 * a.nt + 8;
 	span_cap = (span_cap + 3) & ~3;
