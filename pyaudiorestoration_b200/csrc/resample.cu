@@ -587,7 +587,18 @@ sinc_kernel(const __grid_constant__ SincArgs a, const __grid_constant__ SincTab<
 #define SINC_WS_PWARPS 4
 #endif
 #ifndef SINC_WS_UNROLL
-#define SINC_WS_UNROLL 4
+#define SINC_WS_UNROLL 2
+#endif
+// Registers after the role split (setmaxnreg; per scheduler 3 * C + P <= 512): the interpolating warps run the block
+// loop unrolled twice with 152, the set-up warps need 56.  Measured: 5.80 vs 5.94 ms against 128 / 128, unroll 1.
+#ifndef SINC_WS_REGS_C
+#define SINC_WS_REGS_C 152
+#endif
+#ifndef SINC_WS_REGS_P
+#define SINC_WS_REGS_P 56
+#endif
+#ifndef SINC_WS_BLOCK_UNROLL
+#define SINC_WS_BLOCK_UNROLL 2
 #endif
 constexpr int WS_CT = 32 * SINC_WS_CWARPS, WS_PT = 32 * SINC_WS_PWARPS, WS_THREADS = WS_CT + WS_PT;
 constexpr int WS_TILE = 2 * WS_CT - 16;
@@ -650,7 +661,7 @@ sinc_kernel_ws(const __grid_constant__ SincArgs a, const __grid_constant__ SincT
 
 	if (tid >= WS_CT) {
 		// =============================== set-up warps ===============================
-#ifdef SINC_WS_REGS_P
+#if SINC_WS_REGS_P > 0
 		asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SINC_WS_REGS_P));
 #endif
 		const int pt = tid - WS_CT, lane = pt & 31, pw = pt >> 5;
@@ -801,7 +812,7 @@ sinc_kernel_ws(const __grid_constant__ SincArgs a, const __grid_constant__ SincT
 	}
 
 	// =============================== interpolating warps ===============================
-#ifdef SINC_WS_REGS_C
+#if SINC_WS_REGS_C > 0
 	asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SINC_WS_REGS_C));
 #endif
 	for (int64_t w = w0; w < w1; w++) {
@@ -826,8 +837,8 @@ sinc_kernel_ws(const __grid_constant__ SincArgs a, const __grid_constant__ SincT
 			const SincSlotRef sl[2] = {{&tb.s[iE], &tb.fc[iE], &tb.g[iE], &tb.sfx[iE]}, {&tb.s[iO], &tb.fc[iO], &tb.g[iO], &tb.sfx[iO]}};
 			float y[2][CH];
 			const SincWin<CH> xu{xs + ((SINC_XFRONT + j0) >> 1) * CH, (xpitch / 2) * CH};
-			if (lowpass) sinc_unit<CH, true, 2, CAP>(nt, tab, xu, sl, y);
-			else sinc_unit<CH, false, 2, CAP>(nt, tab, xu, sl, y);
+			if (lowpass) sinc_unit<CH, true, 2, CAP, SINC_WS_BLOCK_UNROLL>(nt, tab, xu, sl, y);
+			else sinc_unit<CH, false, 2, CAP, SINC_WS_BLOCK_UNROLL>(nt, tab, xu, sl, y);
 #pragma unroll
 			for (int c = 0; c < CH; c++) {
 				if (ch0 + c < a.n_ch) {

@@ -322,7 +322,7 @@ SC_HD void sinc_block(int b, const SincTab<CAP> &tab, const SincWin<CH> &x,
 // All taps of the R outputs of one thread.  Summation order: the weights decay like 1/|d| away from the
 // centre tap, so each half of the tap run is accumulated from its far end towards the centre (small terms
 // first) in its own accumulator; the centre tap comes last.
-template <int CH, bool LOWPASS, int R, int CAP>
+template <int CH, bool LOWPASS, int R, int CAP, int UNROLL = SINC_BLOCK_UNROLL>
 SC_HD void sinc_unit(int nt, const SincTab<CAP> &tab, const SincWin<CH> &x,
                      const SincSlotRef (&sl)[R], float (&out)[R][CH]) {
 	const int nblk = sinc_num_blocks(nt);
@@ -335,7 +335,7 @@ SC_HD void sinc_unit(int nt, const SincTab<CAP> &tab, const SincWin<CH> &x,
 		A[r].sar = A[r].sal = 0.f; A[r].car = 1.f; A[r].ncal = -1.f;
 		if (LOWPASS) rot[r].build(*sl[r].g_fx);
 	}
-	constexpr int kUnroll = SINC_BLOCK_UNROLL;
+	constexpr int kUnroll = UNROLL;
 #pragma unroll kUnroll
 	for (int b = nblk - 1; b >= 0; b--) {
 		if (LOWPASS) {
