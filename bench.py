@@ -732,8 +732,9 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": roof(bytes_sinc, k_sinc, "sinc_kernel",
-                             {"note": "sinc stage is FP32-pipe bound (4.5 / 7.5 FMA-pipe operations per tap at fc = 1 / fc < 1 for "
-                                      "2 channels), not HBM bound; see DESIGN.md",
+                             {"note": "sinc_kernel_ws<2,64> (warp-specialised: 12 interpolating + 4 set-up warps per SM); the stage is "
+                                      "FP32-pipe bound (4.5 / 7.5 FMA-pipe operations per tap at fc = 1 / fc < 1 for 2 channels), "
+                                      "not HBM bound; see DESIGN.md",
                               "taps_per_s": C * m * 2 * NT / (k_sinc * 1e-3)}),
             "roofline_stft": roof(bytes_stft, k_stft, "stft_kernel",
                                   {"note": "stft_tma_kernel<11,0>: TMA-staged frames, HBM-bound by design"}),

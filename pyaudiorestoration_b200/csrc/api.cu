@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <chrono>
 #include <map>
 #include <mutex>
 #include <string>
@@ -218,6 +219,23 @@ struct DevBuf {
 	}
 	~DevBuf() { if (p) cudaFreeAsync(p, st); }
 	template <class T> T *as() { return (T *)p; }
+};
+
+// $PAR_B200_TRACE=1: host-side time stamps of a call's phases on stderr (development aid)
+struct CallTrace {
+	bool on;
+	const char *name;
+	std::chrono::steady_clock::time_point t0;
+	explicit CallTrace(const char *n) : name(n) {
+		static const bool enabled = [] { const char *e = getenv("PAR_B200_TRACE"); return e && e[0] == '1'; }();
+		on = enabled;
+		if (on) t0 = std::chrono::steady_clock::now();
+	}
+	void mark(const char *what) const {
+		if (!on) return;
+		const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+		fprintf(stderr, "[par trace] %s: %s +%.3f ms\n", name, what, ms);
+	}
 };
 
 struct EventTimer {
@@ -494,6 +512,7 @@ PAR_API int par_stft_f32(const float *x, int64_t n, int64_t x_stride, int n_ch, 
 	// host pointers: chunks of frames flow through upload -> (de-interleave) -> transform -> download
 	// on three streams, so the PCIe copies in both directions overlap each other and the kernels
 	const size_t esz = mag ? sizeof(float) : sizeof(float2);
+	CallTrace tr("stft");
 	DevBuf dplanar(st), dout(st);
 	AudioUploader up(st);
 	SideStreams ss;
@@ -511,6 +530,7 @@ PAR_API int par_stft_f32(const float *x, int64_t n, int64_t x_stride, int n_ch, 
 	const int64_t half = n_fft / 2;
 	EventTimer tm(st);
 	tm.start();
+	tr.mark("allocated, streams ready");
 	int64_t planar_done = 0;
 	for (int64_t t0 = 0; t0 < T; t0 += per_chunk) {
 		const int64_t t1 = t0 + per_chunk < T ? t0 + per_chunk : T;
@@ -542,9 +562,11 @@ PAR_API int par_stft_f32(const float *x, int64_t n, int64_t x_stride, int n_ch, 
 		}
 	}
 	tm.stop();
+	tr.mark("all chunks enqueued");
 	if ((rc = ss.drain()) != PAR_OK) return rc;
 	PAR_CUDA(cudaStreamSynchronize(st));
 	tm.finish();
+	tr.mark("drained");
 	return PAR_OK;
 }
 
@@ -1015,6 +1037,7 @@ static int resample_with_dev_pos(bool sinc, const double *dpos, int64_t m, const
 		a.out = out; a.out_stride = out_stride; a.out_ch_stride = out_ch_stride;
 		return sinc ? launch_sinc(a, device, st) : launch_linear(a, device, st);
 	}
+	CallTrace tr("resample");
 	DevBuf dout(st);
 	AudioUploader up(st);
 	DevOut dd;
@@ -1028,6 +1051,7 @@ static int resample_with_dev_pos(bool sinc, const double *dpos, int64_t m, const
 	a.out = dd.p; a.out_stride = dd.stride; a.out_ch_stride = dd.ch_stride;
 	EventTimer tm(st);
 	tm.start();
+	tr.mark("allocated, streams ready");
 	int64_t per_chunk = chunk_bytes() / (int64_t)(sizeof(float) * n_ch);
 	if (per_chunk < 1024) per_chunk = 1024;
 	const bool pipelined = chain && monotone && m > 2 * per_chunk;
@@ -1060,9 +1084,11 @@ static int resample_with_dev_pos(bool sinc, const double *dpos, int64_t m, const
 		}
 	}
 	tm.stop();
+	tr.mark("all chunks enqueued");
 	if ((rc = ss.drain()) != PAR_OK) return rc;
 	PAR_CUDA(cudaStreamSynchronize(st));
 	tm.finish();
+	tr.mark("drained");
 	return PAR_OK;
 }
 
@@ -1125,9 +1151,11 @@ PAR_API int par_varispeed_f32(const double *sampletimes, const double *speeds, i
 	if (rc != PAR_OK) return rc;
 	if ((rc = use_device(device)) != PAR_OK) return rc;
 	cudaStream_t st = (cudaStream_t)stream;
+	CallTrace tr("varispeed");
 	std::vector<int64_t> seg_n(k - 1);
 	int64_t total = 0;
 	if ((rc = par_speed_segments(sampletimes, speeds, k, seg_n.data(), &total)) != PAR_OK) return rc;
+	tr.mark("segments");
 	// positive finite speeds and non-empty segments => monotone positions => pipelined host path
 	bool monotone = true;
 	for (int64_t i = 0; i < k; i++) monotone = monotone && speeds[i] > 0.0 && speeds[i] < 1e6;
@@ -1142,8 +1170,11 @@ PAR_API int par_varispeed_f32(const double *sampletimes, const double *speeds, i
 		return PAR_ECAPACITY;
 	}
 	if (*m == 0) return PAR_OK;
-	return resample_with_dev_pos(sinc, dpos.as<double>(), *m, signal, n_in, sig_stride, n_ch, sig_ch_stride, nt, out,
-	                             out_stride, out_ch_stride, flags, device, st, &chain, monotone);
+	tr.mark("positions");
+	rc = resample_with_dev_pos(sinc, dpos.as<double>(), *m, signal, n_in, sig_stride, n_ch, sig_ch_stride, nt, out,
+	                           out_stride, out_ch_stride, flags, device, st, &chain, monotone);
+	tr.mark("done");
+	return rc;
 }
 
 // ---- trackers ----------------------------------------------------------------------------------
