@@ -347,7 +347,8 @@ sinc_kernel(const __grid_constant__ SincArgs a, const __grid_constant__ SincTab<
 	// positions of work item w -> tb[buf].pos (asynchronous)
 	auto prefetch_pos = [&](int64_t tile, int buf) {
 		const int64_t i0 = a.out_begin + tile * SINC_TILE;
-		int64_t cnt = a.m - i0;
+		// a shard's positions reach one past its last output (par_resample_range_f32), no further
+		int64_t cnt = (a.out_end + 1 < a.m ? a.out_end + 1 : a.m) - i0;
 		if (cnt > SINC_TILE + 1) cnt = SINC_TILE + 1;
 		for (int e = tid; e < cnt; e += SINC_THREADS) cp_async8(&sm.tb[buf].pos[e], posg + i0 + e);
 	};
@@ -667,14 +668,16 @@ sinc_kernel_ws(const __grid_constant__ SincArgs a, const __grid_constant__ SincT
 		const int pt = tid - WS_CT, lane = pt & 31, pw = pt >> 5;
 		auto prefetch_pos = [&](int64_t tl, int pb) {
 			const int64_t i0 = a.out_begin + tl * WS_TILE;
-			int64_t cnt = a.m - i0;
+			// a shard's positions reach one past its last output (par_resample_range_f32), no further
+			int64_t cnt = (a.out_end + 1 < a.m ? a.out_end + 1 : a.m) - i0;
 			if (cnt > WS_TILE + 1) cnt = WS_TILE + 1;
 			for (int e = pt; e < cnt; e += WS_PT) cp_async8(&sm.pos[pb][e], posg + i0 + e);
 		};
 		prefetch_pos(tile, 0);
 		cp_async_commit();
-		// read period of the last output (the reference repeats the previous one)
-		const double per_tail = a.m >= 2 ? fmax(1e-12, posg[a.m - 1] - posg[a.m - 2]) : 0.0;
+		// read period of the last output (the reference repeats the previous one); only the launch that holds the last
+		// output has those two positions in its slice
+		const double per_tail = (a.out_end >= a.m && a.m >= 2) ? fmax(1e-12, posg[a.m - 1] - posg[a.m - 2]) : 0.0;
 		const bool aligned = a.aligned_edges != 0;
 		for (int64_t w = w0; w < w1; w++) {
 			const int buf = (int)((w - w0) & 1);

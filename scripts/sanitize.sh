@@ -8,3 +8,8 @@ for tool in memcheck racecheck; do
       > gpurun_out/sanitizer_$tool.log 2>&1
   echo "$tool exit=$? : $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|passed|failed' gpurun_out/sanitizer_$tool.log | tail -3 | tr '\n' ' ')"
 done
+# shard entry points with exactly sized slices: without torch's caching allocator every tensor is its own cudaMalloc, so a
+# read one element past a rank's positions / samples slice is an error here (round 2: the resampler's tail-period read)
+PYTORCH_NO_CUDA_MEMORY_CACHING=1 compute-sanitizer --tool memcheck --error-exitcode 7 --print-limit 5 python -m pytest tests -m gpu -q -x \
+    --timeout 1500 -k "test_time_shards or test_shared_segment_sums" > gpurun_out/sanitizer_shards_memcheck.log 2>&1
+echo "shards memcheck exit=$? : $(grep -E 'ERROR SUMMARY|passed|failed' gpurun_out/sanitizer_shards_memcheck.log | tail -2 | tr '\n' ' ')"
