@@ -58,6 +58,9 @@ extern "C" {
 #define PAR_OUT_MAGNITUDE (1u << 1) /* par_stft_f32: write float32 |S| + 1e-7 instead of complex64 */
 #define PAR_SINC_ALIGNED_EDGES (1u << 2) /* par_sinc_resample_f32: do NOT reproduce the reference's
                                             start-edge tap misalignment */
+#define PAR_SINC_KERNEL_TILED (1u << 3) /* resamplers: force the two-CTA-per-SM kernel (default below 64 taps) */
+#define PAR_SINC_KERNEL_WS (1u << 4)    /* resamplers: force the warp-specialised kernel (default from 64 taps);
+                                           both kernels produce identical bits, the flags exist for A/B tests */
 
 /* ---- diagnostics ------------------------------------------------------------------------- */
 PAR_API const char *par_last_error(void);

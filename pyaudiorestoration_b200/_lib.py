@@ -16,6 +16,8 @@ _lib = None
 PAR_DEVICE_PTRS = 1 << 0
 PAR_OUT_MAGNITUDE = 1 << 1
 PAR_SINC_ALIGNED_EDGES = 1 << 2
+PAR_SINC_KERNEL_TILED = 1 << 3
+PAR_SINC_KERNEL_WS = 1 << 4
 PAR_ECAPACITY = -4
 PAR_MODE_LINEAR = 0
 PAR_MODE_SINC = 1

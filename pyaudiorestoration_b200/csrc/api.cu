@@ -1030,6 +1030,7 @@ static int resample_with_dev_pos(bool sinc, const double *dpos, int64_t m, const
 	SincArgs a;
 	a.pos = dpos; a.m = m; a.n_in = n_in; a.n_ch = n_ch; a.nt = nt;
 	a.aligned_edges = (flags & PAR_SINC_ALIGNED_EDGES) ? 1 : 0;
+	a.kernel = (flags & PAR_SINC_KERNEL_WS) ? 2 : ((flags & PAR_SINC_KERNEL_TILED) ? 1 : 0);
 	a.out_begin = 0; a.out_end = m;
 	a.pos_origin = a.sig_origin = a.out_origin = 0;
 	if (flags & PAR_DEVICE_PTRS) {
@@ -1334,6 +1335,7 @@ PAR_API int par_resample_range_f32(const double *pos, int64_t pos_origin, int64_
 	a.pos = pos; a.m = m_global; a.signal = signal; a.n_in = n_in_global; a.sig_stride = 1; a.sig_ch_stride = sig_ch_stride;
 	a.n_ch = n_ch; a.nt = nt; a.out = out; a.out_stride = out_stride; a.out_ch_stride = out_ch_stride;
 	a.aligned_edges = (flags & PAR_SINC_ALIGNED_EDGES) ? 1 : 0;
+	a.kernel = (flags & PAR_SINC_KERNEL_WS) ? 2 : ((flags & PAR_SINC_KERNEL_TILED) ? 1 : 0);
 	a.out_begin = out_begin; a.out_end = out_end;
 	a.pos_origin = pos_origin; a.sig_origin = sig_origin; a.out_origin = out_begin;
 	return sinc ? launch_sinc(a, device, (cudaStream_t)stream) : launch_linear(a, device, (cudaStream_t)stream);

@@ -887,7 +887,8 @@ static const SincTab<CAP> *sinc_param_table(int nt) {
 
 // Which kernel: the warp-specialised one from 64 taps up (measured on B200: 100 taps 3.32 vs 3.75 ms, 256 taps 5.94 vs
 // 6.56 ms; 16 taps 0.27 vs 0.20 ms -- with few taps the set-up warps cannot keep up).  PAR_B200_SINC_WS=0/1 forces one.
-static bool sinc_use_ws(int nt) {
+static bool sinc_use_ws(int nt, int kernel) {
+	if (kernel) return kernel == 2;
 	static const int forced = [] { const char *e = getenv("PAR_B200_SINC_WS"); return e && (e[0] == '0' || e[0] == '1') ? e[0] - '0' : -1; }();
 	if (forced >= 0) return forced == 1;
 	return nt >= 32;
@@ -915,7 +916,7 @@ static int launch_sinc_ws(const SincArgs &a, int device, cudaStream_t st, const 
 
 template <int CH, int CAP>
 static int launch_sinc_ch(const SincArgs &a, int device, cudaStream_t st, const SincTables &tb) {
-	if (sinc_use_ws(a.nt)) return launch_sinc_ws<CH, CAP>(a, device, st, tb);
+	if (sinc_use_ws(a.nt, a.kernel)) return launch_sinc_ws<CH, CAP>(a, device, st, tb);
 	// widest span staged in shared memory: a tile read at up to ~2.5x speed
 	int span_cap = 2 * SINC_TILE + 2 * a.nt + 8;
 	span_cap = (span_cap + 3) & ~3;

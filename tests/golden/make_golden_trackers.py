@@ -1,5 +1,5 @@
 """Golden fixture for the frequency trackers: runs the UNMODIFIED tracker classes of the
-reference's util/wow_detection.py (Peak, Peak Track, Center of Gravity) on a float32 magnitude spectrogram of a
+reference's util/wow_detection.py (Peak, Peak Track, Center of Gravity, Zero-Crossing, Correlation) on a float32 magnitude spectrogram of a
 seeded synthetic wow signal.  matplotlib (imported at module level by the reference, never used by these
 classes) is an inert stub.
 
@@ -46,6 +46,13 @@ def main(ref):
            "spec_checksum": np.array([float(spec.astype(np.float64).sum()), float(spec[300, 100])])}
     for key, name in (("peak", "Peak"), ("peak_track", "Peak Track"), ("cog", "Center of Gravity")):
         tr = wow_detection.wow_detectors[name](spec, x, list(trail), fft_size * zeropad, hop, sr, 1.0, "Linear")
+        out[key + "__times"] = np.asarray(tr.times)
+        out[key + "__freqs"] = np.asarray(tr.freqs)
+        print(name, len(tr.freqs), tr.freqs[:3], float(np.std(tr.freqs)))
+    # the two host-side trackers of the registry that take a waveform / compare neighbouring frames
+    # (Zero-Crossing reads signal[s0:s1, 0]: a (samples, channels) array)
+    for key, name in (("zero_crossing", "Zero-Crossing"), ("correlation", "Correlation")):
+        tr = wow_detection.wow_detectors[name](spec, x[:, None], list(trail), fft_size * zeropad, hop, sr, 1.0, "Linear")
         out[key + "__times"] = np.asarray(tr.times)
         out[key + "__freqs"] = np.asarray(tr.freqs)
         print(name, len(tr.freqs), tr.freqs[:3], float(np.std(tr.freqs)))

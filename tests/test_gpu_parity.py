@@ -953,6 +953,34 @@ def test_sinc_channel_groups(resampling, channels):
     _check_sinc(np.ascontiguousarray(out[:, channels - 1]), pos, np.ascontiguousarray(sig[:, channels - 1]), 64)
 
 
+@pytest.mark.parametrize("nt,channels,speed", [(128, 2, 1.0), (50, 1, 1.0), (64, 4, 1.3), (128, 3, 0.7), (300, 2, 1.0),
+                                               (8, 2, 1.0), (128, 2, 3.2)])
+def test_both_sinc_kernels_give_the_same_bits(par, nt, channels, speed):
+    """The resampler has two kernels (csrc/resample.cu: `sinc_kernel`, every warp sets up and interpolates; and
+    `sinc_kernel_ws`, set-up warps feeding interpolating warps).  Records, units and tap arithmetic are shared, so their
+    outputs must be identical arrays -- wow, constant fast / slow speeds (all low-passed / all unpaired outputs), a span
+    wider than the two-CTA kernel stages (3.2x), small and large tap tables -- and both must match the oracle."""
+    from pyaudiorestoration_b200 import _lib
+    L = _lib.lib()
+    sr = 48000
+    n = sr * 2 + 77
+    sig = np.stack([synth(n, 300 + c, sr) for c in range(channels)])                  # planar (channels, n)
+    t = np.arange(0, n, 512, dtype=np.float64)
+    t = np.append(t, float(n))
+    sp = speed * (1.0 + 0.02 * np.sin(2 * np.pi * 3.0 * t / sr))
+    pos = oracle.speed_to_pos_c(t, sp, n)
+    m = len(pos)
+    outs = []
+    for flag in (_lib.PAR_SINC_KERNEL_TILED, _lib.PAR_SINC_KERNEL_WS):
+        out = np.full((channels, m), np.nan, np.float32)
+        rc = L.par_sinc_resample_f32(pos.ctypes.data, m, sig.ctypes.data, n, 1, channels, n, nt, out.ctypes.data, 1, m,
+                                     flag, _lib.device(), None)
+        _lib.check(rc, "par_sinc_resample_f32")
+        outs.append(out)
+    assert np.array_equal(outs[0], outs[1])
+    _check_sinc(outs[1][channels - 1], pos, sig[channels - 1], nt)
+
+
 # ----------------------------------------------------------------------------------------- re-entrancy
 def test_concurrent_calls_from_threads(fourier, resampling):
     """The reference enters this path from QThread workers while the GUI thread calls stft/istft

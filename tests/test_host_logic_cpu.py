@@ -146,4 +146,19 @@ def test_trackers_host_side(double, golden_dir):
     for key, name in (("peak", "Peak"), ("peak_track", "Peak Track"), ("cog", "Center of Gravity")):
         tr = wow_detection.wow_detectors[name](spec, x, list(trail), fft_size * zp, hop, sr, 1.0, "Linear")
         assert np.array_equal(tr.times, z[key + "__times"]) and np.array_equal(tr.freqs, z[key + "__freqs"]), key
-    assert set(wow_detection.wow_detectors) == {"Peak", "Peak Track", "Center of Gravity"}
+    # the host-side members of the registry against the unmodified reference classes (same spectrogram, same trail):
+    # identical scipy calls on identical inputs
+    for key, name in (("zero_crossing", "Zero-Crossing"), ("correlation", "Correlation")):
+        tr = wow_detection.wow_detectors[name](spec, x[:, None], list(trail), fft_size * zp, hop, sr, 1.0, "Linear")
+        assert np.array_equal(tr.times, z[key + "__times"]), key
+        np.testing.assert_allclose(tr.freqs, z[key + "__freqs"], rtol=1e-12, atol=0, err_msg=key)
+    free = wow_detection.wow_detectors["Freehand Draw"](spec, x, list(trail), fft_size * zp, hop, sr)
+    assert np.array_equal(free.freqs, np.interp(free.times, [p[0] for p in trail], [p[1] for p in trail]))
+    assert set(wow_detection.wow_detectors) == {"Peak", "Peak Track", "Center of Gravity", "Zero-Crossing", "Partials",
+                                                "Freehand Draw", "Correlation", "Sine Regression"}
+    # sine regression of a speed curve (pyrespeeder_gui.py:177): recovers a 0.5556 Hz wow of 1 %
+    tt = np.linspace(0, 20, 2000)
+    curve = np.stack((tt, 1 + 0.01 * np.sin(2 * np.pi * 0.5556 * tt + 0.3)), -1)
+    amp, omega, phase, off = wow_detection.trace_sine_reg(curve, 2.0, 18.0, rpm=33.333)
+    assert abs(abs(amp) - 0.01) < 1e-6 and abs(omega / (2 * np.pi) - 0.5556) < 1e-6 and off == 0
+    assert list(wow_detection.zero_crossings(np.array([1.0, -1.0, -2.0, 3.0]))) == [0, 2]
