@@ -272,6 +272,8 @@ def trace_signal(signal, trail, fft_size, hop, sr, mode="Peak", tolerance_st=1, 
     without materialising the spectrogram on the host (or anywhere beyond the traced frames)."""
     L = _lib.lib()
     _lib.require_device()
+    if wow_detectors[mode].mode is None:
+        raise ValueError(f"trace_signal runs the spectral trackers (Peak, Peak Track, Center of Gravity), not {mode!r}")
     keep, ptr, stride = _lib.f32_layout(signal)
     n = len(keep)
     fft_size, hop, zeropad = int(fft_size), int(hop), int(zeropad)
