@@ -418,6 +418,12 @@ static int download_out(const DevOut &o, float *dst, int64_t o0, int64_t o1, int
 
 // bytes of output per pipeline chunk of a host-pointer call ($PAR_B200_CHUNK_BYTES overrides; tests
 // use it to push small inputs through many chunks)
+// $PAR_B200_NO_RAMP=1: full-size first chunks and no early upload (A/B measurements of the host pipelines)
+static bool ramp_enabled() {
+	static const bool on = [] { const char *e = getenv("PAR_B200_NO_RAMP"); return !(e && e[0] == '1'); }();
+	return on;
+}
+
 static int64_t chunk_bytes() {
 	const char *e = getenv("PAR_B200_CHUNK_BYTES");
 	if (e && *e) {
@@ -532,8 +538,11 @@ PAR_API int par_stft_f32(const float *x, int64_t n, int64_t x_stride, int n_ch, 
 	tm.start();
 	tr.mark("allocated, streams ready");
 	int64_t planar_done = 0;
-	for (int64_t t0 = 0; t0 < T; t0 += per_chunk) {
-		const int64_t t1 = t0 + per_chunk < T ? t0 + per_chunk : T;
+	// the first chunks are small (1/8, 1/4, 1/2 of a chunk): the download engine, which bounds the call, starts after
+	// 1/8 of a chunk's upload + transform instead of a whole one
+	int64_t ramp = per_chunk >= 128 && ramp_enabled() ? per_chunk / 8 : per_chunk;
+	for (int64_t t0 = 0, t1; t0 < T; t0 = t1, ramp = ramp * 2 < per_chunk ? ramp * 2 : per_chunk) {
+		t1 = t0 + ramp < T ? t0 + ramp : T;
 		// samples the frames [t0, t1) read: up to (t1-1)*hop - half + n_fft, everything once a frame
 		// reaches the reflected tail (or the signal is short enough to reflect more than once)
 		int64_t need = (t1 - 1) * hop - half + n_fft + 8;
@@ -1025,7 +1034,7 @@ static int resample_with_dev_pos(bool sinc, const double *dpos, int64_t m, const
                                  int64_t sig_stride, int n_ch, int64_t sig_ch_stride, int nt,
                                  float *out, int64_t out_stride, int64_t out_ch_stride,
                                  unsigned flags, int device, cudaStream_t st, const SegChain *chain = nullptr,
-                                 bool monotone = false) {
+                                 bool monotone = false, AudioUploader *pre_up = nullptr, SideStreams *pre_ss = nullptr) {
 	int rc;
 	SincArgs a;
 	a.pos = dpos; a.m = m; a.n_in = n_in; a.n_ch = n_ch; a.nt = nt;
@@ -1040,13 +1049,18 @@ static int resample_with_dev_pos(bool sinc, const double *dpos, int64_t m, const
 	}
 	CallTrace tr("resample");
 	DevBuf dout(st);
-	AudioUploader up(st);
+	AudioUploader up_local(st);
 	DevOut dd;
-	SideStreams ss;
-	if ((rc = up.init(signal, n_in, sig_stride, n_ch, sig_ch_stride)) != PAR_OK) return rc;
+	SideStreams ss_local;
+	// par_varispeed_f32 hands in an uploader that is already sending the head of the signal
+	AudioUploader &up = pre_up ? *pre_up : up_local;
+	SideStreams &ss = pre_ss ? *pre_ss : ss_local;
+	if (!pre_up && (rc = up.init(signal, n_in, sig_stride, n_ch, sig_ch_stride)) != PAR_OK) return rc;
 	if ((rc = alloc_out(dout, m, out_stride, n_ch, out_ch_stride, st, &dd)) != PAR_OK) return rc;
-	if ((rc = ss.init()) != PAR_OK) return rc;
-	if ((rc = ss.after(ss.up, st)) != PAR_OK) return rc;
+	if (!pre_ss) {
+		if ((rc = ss.init()) != PAR_OK) return rc;
+		if ((rc = ss.after(ss.up, st)) != PAR_OK) return rc;
+	}
 	const DevAudio da = up.view();
 	a.signal = da.p; a.sig_stride = da.stride; a.sig_ch_stride = da.ch_stride;
 	a.out = dd.p; a.out_stride = dd.stride; a.out_ch_stride = dd.ch_stride;
@@ -1065,9 +1079,10 @@ static int resample_with_dev_pos(bool sinc, const double *dpos, int64_t m, const
 	} else {
 		const int64_t n_seg = (int64_t)chain->start.size();
 		int64_t seg = 0, o0 = 0;
-		while (o0 < m) {
-			// advance to the first segment start at least per_chunk outputs ahead
-			while (seg < n_seg && chain->start[seg] < o0 + per_chunk) seg++;
+		int64_t ramp = per_chunk / 8 > 1024 && ramp_enabled() ? per_chunk / 8 : per_chunk;     // small first chunks: see par_stft_f32
+		for (; o0 < m; ramp = ramp * 2 < per_chunk ? ramp * 2 : per_chunk) {
+			// advance to the first segment start at least `ramp` outputs ahead
+			while (seg < n_seg && chain->start[seg] < o0 + ramp) seg++;
 			int64_t o1 = m, need = n_in;
 			if (seg < n_seg && chain->start[seg] < m) {
 				o1 = chain->start[seg];
@@ -1163,7 +1178,17 @@ PAR_API int par_varispeed_f32(const double *sampletimes, const double *speeds, i
 	for (int64_t i = 0; i + 1 < k; i++) monotone = monotone && seg_n[i] >= 2;
 	DevBuf dpos(st);
 	SegChain chain;
+	AudioUploader up(st);          // declared behind dpos: destroyed (and its streams drained) before it is freed
+	SideStreams ss;
+	const bool host_io = !(flags & PAR_DEVICE_PTRS) && n_in > 0 && signal;
 	if ((rc = dpos.alloc((size_t)(total > 0 ? total : 1) * sizeof(double))) != PAR_OK) return rc;
+	if (host_io) {
+		// the head of the signal crosses PCIe while the positions are being expanded
+		if ((rc = up.init(signal, n_in, sig_stride, n_ch, sig_ch_stride)) != PAR_OK) return rc;
+		if ((rc = ss.init()) != PAR_OK) return rc;
+		if ((rc = ss.after(ss.up, st)) != PAR_OK) return rc;       // allocations are stream-ordered on st
+		if (ramp_enabled() && (rc = up.upload_to(4 << 20, ss.up)) != PAR_OK) return rc;
+	}
 	rc = positions_device(sampletimes, speeds, k, (double)n_in, seg_n, total, dpos.as<double>(), total, m, st, &chain);
 	if (rc != PAR_OK) return rc;
 	if (*m > out_cap) {
@@ -1173,7 +1198,8 @@ PAR_API int par_varispeed_f32(const double *sampletimes, const double *speeds, i
 	if (*m == 0) return PAR_OK;
 	tr.mark("positions");
 	rc = resample_with_dev_pos(sinc, dpos.as<double>(), *m, signal, n_in, sig_stride, n_ch, sig_ch_stride, nt, out,
-	                           out_stride, out_ch_stride, flags, device, st, &chain, monotone);
+	                           out_stride, out_ch_stride, flags, device, st, &chain, monotone, host_io ? &up : nullptr,
+	                           host_io ? &ss : nullptr);
 	tr.mark("done");
 	return rc;
 }
