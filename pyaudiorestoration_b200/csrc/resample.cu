@@ -333,10 +333,10 @@ sinc_kernel(const __grid_constant__ SincArgs a, const __grid_constant__ SincTab<
 	const int64_t tiles = (a.out_end - a.out_begin + SINC_TILE - 1) / SINC_TILE;
 	const int groups = (a.n_ch + CH - 1) / CH;
 	const int64_t work = tiles * groups;
-	// contiguous work ranges: consecutive tiles of a CTA are neighbours in memory
-	const int64_t per_cta = (work + gridDim.x - 1) / gridDim.x;
-	const int64_t w0 = (int64_t)blockIdx.x * per_cta;
-	const int64_t w1 = w0 + per_cta < work ? w0 + per_cta : work;
+	// work items are dealt round-robin (item j of this CTA is work item blockIdx.x + j * gridDim.x): all CTAs sit on the
+	// same phase of the speed curve at any time, so stretches of low-passed outputs do not pile up on a few of them
+	const int64_t w0 = 0;
+	const int64_t w1 = (int64_t)blockIdx.x < work ? (work - 1 - blockIdx.x) / gridDim.x + 1 : 0;
 	if (w0 >= w1) return;
 	const double *posg = a.pos - a.pos_origin;
 	for (int e = tid; e < 2 * CH * SINC_XFRONT; e += SINC_THREADS) {          // front padding of both buffers (both parity planes)
@@ -482,9 +482,9 @@ sinc_kernel(const __grid_constant__ SincArgs a, const __grid_constant__ SincTab<
 	};
 
 	// (group, tile) of the work items w, w + 1, w + 2, advanced without 64-bit divisions
-	int grp0 = (int)(w0 / tiles);
-	int64_t tile0 = w0 - (int64_t)grp0 * tiles;
-	auto advance = [&](int &g, int64_t &t) { if (++t == tiles) { t = 0; g++; } };
+	int grp0 = (int)((int64_t)blockIdx.x / tiles);
+	int64_t tile0 = (int64_t)blockIdx.x - (int64_t)grp0 * tiles;
+	auto advance = [&](int &g, int64_t &t) { t += gridDim.x; while (t >= tiles) { t -= tiles; g++; } };
 	int grp1 = grp0, grp2;
 	int64_t tile1 = tile0, tile2;
 	advance(grp1, tile1);
@@ -642,9 +642,12 @@ sinc_kernel_ws(const __grid_constant__ SincArgs a, const __grid_constant__ SincT
 	const int64_t tiles = (a.out_end - a.out_begin + WS_TILE - 1) / WS_TILE;
 	const int groups = (a.n_ch + CH - 1) / CH;
 	const int64_t work = tiles * groups;
-	const int64_t per_cta = (work + gridDim.x - 1) / gridDim.x;
-	const int64_t w0 = (int64_t)blockIdx.x * per_cta;
-	const int64_t w1 = w0 + per_cta < work ? w0 + per_cta : work;
+	// Work items (tile, channel group) are dealt round-robin: at any moment the CTAs work on neighbouring tiles, i.e. on
+	// the same phase of the speed curve, so stretches of low-passed outputs (which cost ~1.6x) do not pile up on a few
+	// CTAs the way they do with one contiguous range per CTA; neighbours also find each other's tap halo in L2.
+	// w0 / w1 count this CTA's items: item j is work item blockIdx.x + j * gridDim.x.
+	const int64_t w0 = 0;
+	const int64_t w1 = (int64_t)blockIdx.x < work ? (work - 1 - blockIdx.x) / gridDim.x + 1 : 0;
 	if (w0 >= w1) return;
 	const double *posg = a.pos - a.pos_origin;
 	for (int e = tid; e < 2 * CH * SINC_XFRONT; e += WS_THREADS) {
@@ -657,8 +660,8 @@ sinc_kernel_ws(const __grid_constant__ SincArgs a, const __grid_constant__ SincT
 		t.rec[e] = 0u; t.s[e] = 0.5f; t.fc[e] = 1.f; t.g[e] = 0; t.sfx[e] = 0;
 	}
 	__syncthreads();
-	int grp = (int)(w0 / tiles);
-	int64_t tile = w0 - (int64_t)grp * tiles;
+	int grp = (int)((int64_t)blockIdx.x / tiles);
+	int64_t tile = (int64_t)blockIdx.x - (int64_t)grp * tiles;
 
 	if (tid >= WS_CT) {
 		// =============================== set-up warps ===============================
@@ -684,8 +687,8 @@ sinc_kernel_ws(const __grid_constant__ SincArgs a, const __grid_constant__ SincT
 			WsTileBuf &tb = sm.tb[buf];
 			const double *tpos = sm.pos[buf];
 			int grp_n = grp;
-			int64_t tile_n = tile;
-			if (++tile_n == tiles) { tile_n = 0; grp_n++; }
+			int64_t tile_n = tile + gridDim.x;
+			while (tile_n >= tiles) { tile_n -= tiles; grp_n++; }
 			cp_async_wait_all();                                   // positions of this tile (issued a tile ago)
 			named_sync(WS_BAR_PROD, WS_PT);
 			if (w + 1 < w1) prefetch_pos(tile_n, buf ^ 1);         // pos[buf ^ 1] was last read two barriers ago
