@@ -1034,7 +1034,8 @@ static int resample_with_dev_pos(bool sinc, const double *dpos, int64_t m, const
                                  int64_t sig_stride, int n_ch, int64_t sig_ch_stride, int nt,
                                  float *out, int64_t out_stride, int64_t out_ch_stride,
                                  unsigned flags, int device, cudaStream_t st, const SegChain *chain = nullptr,
-                                 bool monotone = false, AudioUploader *pre_up = nullptr, SideStreams *pre_ss = nullptr) {
+                                 bool monotone = false, AudioUploader *pre_up = nullptr, SideStreams *pre_ss = nullptr,
+                                 double period_dev = -1.0) {
 	int rc;
 	SincArgs a;
 	a.pos = dpos; a.m = m; a.n_in = n_in; a.n_ch = n_ch; a.nt = nt;
@@ -1042,6 +1043,7 @@ static int resample_with_dev_pos(bool sinc, const double *dpos, int64_t m, const
 	a.kernel = (flags & PAR_SINC_KERNEL_WS) ? 2 : ((flags & PAR_SINC_KERNEL_TILED) ? 1 : 0);
 	a.out_begin = 0; a.out_end = m;
 	a.pos_origin = a.sig_origin = a.out_origin = 0;
+	a.period_dev = period_dev;
 	if (flags & PAR_DEVICE_PTRS) {
 		a.signal = signal; a.sig_stride = sig_stride; a.sig_ch_stride = sig_ch_stride;
 		a.out = out; a.out_stride = out_stride; a.out_ch_stride = out_ch_stride;
@@ -1174,7 +1176,13 @@ PAR_API int par_varispeed_f32(const double *sampletimes, const double *speeds, i
 	tr.mark("segments");
 	// positive finite speeds and non-empty segments => monotone positions => pipelined host path
 	bool monotone = true;
-	for (int64_t i = 0; i < k; i++) monotone = monotone && speeds[i] > 0.0 && speeds[i] < 1e6;
+	double period_dev = 0.0;           // largest |read period - 1| on the curve: sizes the resampler's tiles
+	for (int64_t i = 0; i < k; i++) {
+		monotone = monotone && speeds[i] > 0.0 && speeds[i] < 1e6;
+		const double d = fabs(1.0 / speeds[i] - 1.0);
+		if (d > period_dev) period_dev = d;
+	}
+	if (!(period_dev < 1e6)) period_dev = -1.0;
 	for (int64_t i = 0; i + 1 < k; i++) monotone = monotone && seg_n[i] >= 2;
 	DevBuf dpos(st);
 	SegChain chain;
@@ -1199,7 +1207,7 @@ PAR_API int par_varispeed_f32(const double *sampletimes, const double *speeds, i
 	tr.mark("positions");
 	rc = resample_with_dev_pos(sinc, dpos.as<double>(), *m, signal, n_in, sig_stride, n_ch, sig_ch_stride, nt, out,
 	                           out_stride, out_ch_stride, flags, device, st, &chain, monotone, host_io ? &up : nullptr,
-	                           host_io ? &ss : nullptr);
+	                           host_io ? &ss : nullptr, period_dev);
 	tr.mark("done");
 	return rc;
 }

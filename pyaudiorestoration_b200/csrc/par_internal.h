@@ -91,6 +91,7 @@ struct SincArgs {
 	int64_t out_stride, out_ch_stride;
 	int aligned_edges;
 	int kernel = 0;               // 0: by tap count, 1: two-CTA tiled kernel, 2: warp-specialised kernel
+	double period_dev = -1.0;     // largest |read period - 1| the caller expects (tile sizing of the resampler); < 0: unknown
 	int64_t out_begin, out_end;   // output range handled by this launch, [0, m) for all of it
 	// shards: pos[0] is position `pos_origin`, signal[0] is sample `sig_origin`, out[0] is output `out_origin`
 	int64_t pos_origin, sig_origin, out_origin;

@@ -621,25 +621,42 @@ struct WsTileBuf {
 	int unit[WS_TILE];              // first output of the unit | paired << 16
 	long long i0;
 	int n_units, ch0, adj, staged;  // centre index in the staged span = (rec >> 3) + adj
+	int rot, pad_;                  // unit u belongs to interpolating thread (u + rot) % WS_CT
 };
 struct WsSmem {
 	WsTileBuf tb[2];
 	double pos[2][WS_TILE + 2];
 	int red[2][SINC_WS_PWARPS];
 	int wsum[SINC_WS_PWARPS];
+	unsigned long long full_bar[2]; // mbarriers: tile buffer b is ready (the set-up threads arrive, the others only wait)
 };
+
+__device__ __forceinline__ void ws_mbar_init(unsigned long long *bar, int count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ws_mbar_arrive(unsigned long long *bar) {
+	asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ bool ws_mbar_test(unsigned long long *bar, unsigned parity) {
+	unsigned ok;
+	asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+	             : "=r"(ok) : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+	return ok != 0;
+}
 
 template <int CH, int CAP>
 __global__ void __launch_bounds__(WS_THREADS, 1)
 sinc_kernel_ws(const __grid_constant__ SincArgs a, const __grid_constant__ SincTab<CAP> tab,
-               const float *__restrict__ ctab, const float *__restrict__ hptab, const int span_cap) {
+               const float *__restrict__ ctab, const float *__restrict__ hptab, const int span_cap, const int TL) {
+	// TL <= WS_TILE: outputs per tile of this launch, chosen by the host so that a tile's units fill one round of the
+	// interpolating threads at the expected read period (launch_sinc_ws)
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	WsSmem &sm = *reinterpret_cast<WsSmem *>(smem_raw);
 	float *xs_all = reinterpret_cast<float *>(smem_raw + ((sizeof(WsSmem) + 15) & ~(size_t)15));
 	const int xpitch = SINC_XFRONT + span_cap + SINC_XPAD;
 	const int nt = a.nt;
 	const int tid = threadIdx.x;
-	const int64_t tiles = (a.out_end - a.out_begin + WS_TILE - 1) / WS_TILE;
+	const int64_t tiles = (a.out_end - a.out_begin + TL - 1) / TL;
 	const int groups = (a.n_ch + CH - 1) / CH;
 	const int64_t work = tiles * groups;
 	// Work items (tile, channel group) are dealt round-robin: at any moment the CTAs work on neighbouring tiles, i.e. on
@@ -654,10 +671,16 @@ sinc_kernel_ws(const __grid_constant__ SincArgs a, const __grid_constant__ SincT
 		const int bufi = e / (CH * SINC_XFRONT), r = e % (CH * SINC_XFRONT), par = r / (CH * SINC_XFRONT / 2), q = r % (CH * SINC_XFRONT / 2);
 		xs_all[bufi * CH * xpitch + par * (xpitch / 2) * CH + q] = 0.f;
 	}
+	if (tid == 0) {
+		ws_mbar_init(&sm.full_bar[0], WS_PT);
+		ws_mbar_init(&sm.full_bar[1], WS_PT);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
 	if (tid < 4) {
 		WsTileBuf &t = sm.tb[tid >> 1];
 		const int e = WS_TILE + (tid & 1);
-		t.rec[e] = 0u; t.s[e] = 0.5f; t.fc[e] = 1.f; t.g[e] = 0; t.sfx[e] = 0;
+		t.rec[TL + (tid & 1)] = 0u;          // the unit scan looks one output past the tile
+		t.s[e] = 0.5f; t.fc[e] = 1.f; t.g[e] = 0; t.sfx[e] = 0;
 	}
 	__syncthreads();
 	int grp = (int)((int64_t)blockIdx.x / tiles);
@@ -670,10 +693,10 @@ sinc_kernel_ws(const __grid_constant__ SincArgs a, const __grid_constant__ SincT
 #endif
 		const int pt = tid - WS_CT, lane = pt & 31, pw = pt >> 5;
 		auto prefetch_pos = [&](int64_t tl, int pb) {
-			const int64_t i0 = a.out_begin + tl * WS_TILE;
+			const int64_t i0 = a.out_begin + tl * TL;
 			// a shard's positions reach one past its last output (par_resample_range_f32), no further
 			int64_t cnt = (a.out_end + 1 < a.m ? a.out_end + 1 : a.m) - i0;
-			if (cnt > WS_TILE + 1) cnt = WS_TILE + 1;
+			if (cnt > TL + 1) cnt = TL + 1;
 			for (int e = pt; e < cnt; e += WS_PT) cp_async8(&sm.pos[pb][e], posg + i0 + e);
 		};
 		prefetch_pos(tile, 0);
@@ -682,6 +705,7 @@ sinc_kernel_ws(const __grid_constant__ SincArgs a, const __grid_constant__ SincT
 		// output has those two positions in its slice
 		const double per_tail = (a.out_end >= a.m && a.m >= 2) ? fmax(1e-12, posg[a.m - 1] - posg[a.m - 2]) : 0.0;
 		const bool aligned = a.aligned_edges != 0;
+		int rot = 0;
 		for (int64_t w = w0; w < w1; w++) {
 			const int buf = (int)((w - w0) & 1);
 			WsTileBuf &tb = sm.tb[buf];
@@ -694,7 +718,7 @@ sinc_kernel_ws(const __grid_constant__ SincArgs a, const __grid_constant__ SincT
 			if (w + 1 < w1) prefetch_pos(tile_n, buf ^ 1);         // pos[buf ^ 1] was last read two barriers ago
 			cp_async_commit();
 			if (w >= w0 + 2) named_sync(WS_BAR_EMPTY + buf, WS_THREADS);   // tile w - 2 has left this buffer
-			const int64_t i0 = a.out_begin + tile * WS_TILE;
+			const int64_t i0 = a.out_begin + tile * TL;
 			double rf = rint(tpos[0]);
 			if (!(rf > -9.0e15)) rf = -9.0e15;
 			if (rf > 9.0e15) rf = 9.0e15;
@@ -703,7 +727,7 @@ sinc_kernel_ws(const __grid_constant__ SincArgs a, const __grid_constant__ SincT
 			// pass 1: the float64 set-up of every output, straight-line so that the unrolled iterations interleave
 			// (outputs behind the end of the range are set up from whatever the buffer holds and marked dead)
 #pragma unroll kWsUnroll
-			for (int o = pt; o < WS_TILE; o += WS_PT) {
+			for (int o = pt; o < TL; o += WS_PT) {
 				const int64_t i = i0 + o;
 				const double p = tpos[o];
 				const double per = i + 1 < a.m ? fmax(1e-12, tpos[o + 1] - p) : per_tail;
@@ -766,7 +790,7 @@ sinc_kernel_ws(const __grid_constant__ SincArgs a, const __grid_constant__ SincT
 #pragma unroll
 			for (int j = 0; j < WS_PER + 2; j++) {
 				const int o = c0 - 1 + j;
-				wd[j] = (o >= 0 && o <= WS_TILE) ? tb.rec[o] : 0u;
+				wd[j] = (o >= 0 && o <= TL) ? tb.rec[o] : 0u;
 			}
 			unsigned starts = 0u, heads = 0u;
 			if (staged) {
@@ -780,7 +804,7 @@ sinc_kernel_ws(const __grid_constant__ SincArgs a, const __grid_constant__ SincT
 					const unsigned k0 = wd[j] >> 3, k1 = wd[j + 1] >> 3;
 					const bool h = (wd[j] & wd[j + 1] & SO_FAST) && !((k0 + (unsigned)adj) & 1u) && k1 == k0 + 1 &&
 					               !((wd[j] ^ wd[j + 1]) & SO_LOWPASS);
-					if (c0 + j - 1 < WS_TILE) {
+					if (c0 + j - 1 < TL) {
 						if ((wd[j] & SO_FAST) && !hprev) starts |= 1u << (j - 1);
 						if (h) heads |= 1u << (j - 1);
 					}
@@ -808,10 +832,15 @@ sinc_kernel_ws(const __grid_constant__ SincArgs a, const __grid_constant__ SincT
 				starts &= starts - 1;
 				tb.unit[idx++] = (c0 + j) | (((heads >> j) & 1u) ? 0x10000 : 0);
 			}
-			if (pt == 0) { tb.i0 = i0; tb.n_units = total; tb.ch0 = grp * CH; tb.adj = adj; tb.staged = staged ? 1 : 0; }
+			if (pt == 0) {
+				tb.i0 = i0; tb.n_units = total; tb.ch0 = grp * CH; tb.adj = adj; tb.staged = staged ? 1 : 0;
+				// the units beyond a full round go to a different set of threads every tile
+				tb.rot = rot;
+				rot = (rot + total) % WS_CT;
+			}
 			cp_async_wait_all();                                    // the span (and the next positions) have landed
 			__threadfence_block();
-			named_arrive(WS_BAR_FULL + buf, WS_THREADS);
+			ws_mbar_arrive(&sm.full_bar[buf]);
 			grp = grp_n; tile = tile_n;
 		}
 		return;
@@ -823,13 +852,16 @@ sinc_kernel_ws(const __grid_constant__ SincArgs a, const __grid_constant__ SincT
 #endif
 	for (int64_t w = w0; w < w1; w++) {
 		const int buf = (int)((w - w0) & 1);
-		named_sync(WS_BAR_FULL + buf, WS_THREADS);
+		// no barrier among the interpolating warps: a warp moves on as soon as ITS units of the tile are done
+		while (!ws_mbar_test(&sm.full_bar[buf], (unsigned)(((w - w0) >> 1) & 1))) {}
 		const WsTileBuf &tb = sm.tb[buf];
 		const float *xs = xs_all + buf * CH * xpitch;
 		const int64_t i0 = tb.i0;
 		const int n_units = tb.n_units, ch0 = tb.ch0, adj = tb.adj;
+		int u_first = tid - tb.rot;
+		if (u_first < 0) u_first += WS_CT;
 		const bool staged = tb.staged != 0;
-		for (int u = tid; u < n_units; u += WS_CT) {
+		for (int u = u_first; u < n_units; u += WS_CT) {
 			const int code = tb.unit[u];
 			const int o = code & 0xffff;
 			const bool paired = (code >> 16) != 0;
@@ -854,7 +886,7 @@ sinc_kernel_ws(const __grid_constant__ SincArgs a, const __grid_constant__ SincT
 				}
 			}
 		}
-		for (int o = tid; o < WS_TILE; o += WS_CT) {
+		for (int o = tid; o < TL; o += WS_CT) {
 			const unsigned fl = tb.rec[o];
 			if ((fl & SO_LIVE) && !((fl & SO_FAST) && staged)) {
 				const int64_t i = i0 + o;
@@ -905,13 +937,21 @@ static int launch_sinc_ws(const SincArgs &a, int device, cudaStream_t st, const 
 	const int smem = (int)((sizeof(WsSmem) + 15) & ~(size_t)15) + 2 * CH * (SINC_XFRONT + span_cap + SINC_XPAD) * (int)sizeof(float);
 	auto kern = sinc_kernel_ws<CH, CAP>;
 	PAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-	const int64_t tiles = (a.out_end - a.out_begin + WS_TILE - 1) / WS_TILE;
+	// Outputs per tile.  Consecutive outputs pair into one unit only while the read position advances by about one
+	// sample: a tile of T outputs holds ~T/2 * (1 + |period - 1|) units (T at twice the speed).  A few units more than
+	// interpolating threads would cost a whole extra round, so the tile is sized for the largest period deviation the
+	// caller expects (the speed curve's, when there is one; else the average over the job plus a margin).
+	double dev = a.period_dev >= 0.0 ? a.period_dev : fabs((double)a.n_in / (double)(a.m > 0 ? a.m : 1) - 1.0) + 0.01;
+	if (!(dev < 1.0)) dev = 1.0;
+	int tile_len = (int)(2.0 * WS_CT / (1.0 + dev)) - 8;
+	tile_len = tile_len < 64 ? 64 : (tile_len > WS_TILE ? WS_TILE : tile_len);
+	const int64_t tiles = (a.out_end - a.out_begin + tile_len - 1) / tile_len;
 	const int64_t work = tiles * ((a.n_ch + CH - 1) / CH);
 	int64_t grid = sm_count(device);
 	if (grid > work) grid = work;
 	if (grid < 1) return PAR_OK;
 	const SincTab<CAP> *pt = sinc_param_table<CAP>(a.nt);
-	kern<<<(unsigned)grid, WS_THREADS, smem, st>>>(a, *pt, tb.c, tb.hp, span_cap);
+	kern<<<(unsigned)grid, WS_THREADS, smem, st>>>(a, *pt, tb.c, tb.hp, span_cap, tile_len);
 	count_launch();
 	PAR_CUDA(cudaGetLastError());
 	return PAR_OK;

@@ -61,6 +61,8 @@ case("wow 150 s 4 ch", sr * 150, 4, 128, wow)
 case("wow 150 s 3 ch", sr * 150, 3, 128, wow)
 case("fast 1.3x (lowpass)", sr * 120, 2, 128, lambda u: 1.3 + 0.05 * np.sin(2 * np.pi * 9 * u))
 case("slow 0.7x", sr * 120, 2, 128, lambda u: 0.7 + 0.05 * np.sin(2 * np.pi * 9 * u))
+case("1.03x + wow", sr * 300, 2, 128, lambda u: 1.03 + 0.003 * np.sin(2 * np.pi * 40 * u))
+case("0.95x + wow", sr * 300, 2, 128, lambda u: 0.95 + 0.003 * np.sin(2 * np.pi * 40 * u))
 case("mixed 0.5..2.6x", sr * 60, 2, 128, lambda u: 1.55 + 1.05 * np.sin(2 * np.pi * 5 * u))
 case("3.5x (span over cap)", sr * 60, 2, 128, lambda u: 3.5 + 0 * u)
 case("short 3000 samples", 3000, 2, 128, wow)
