@@ -920,8 +920,9 @@ static const SincTab<CAP> *sinc_param_table(int nt) {
 	return it->second.get();
 }
 
-// Which kernel: the warp-specialised one from 64 taps up (measured on B200: 100 taps 3.32 vs 3.75 ms, 256 taps 5.94 vs
-// 6.56 ms; 16 taps 0.27 vs 0.20 ms -- with few taps the set-up warps cannot keep up).  PAR_B200_SINC_WS=0/1 forces one.
+// Which kernel: the warp-specialised one from 64 taps (NT 32) up.  Measured on B200, 300 s x 2 ch at 96 kHz, two-CTA vs
+// warp-specialised: NT 16: 0.99 / 1.08 ms, 24: 1.11 / 1.13, 32: 1.22 / 1.19, 40: 1.33 / 1.25, 50: 1.58 / 1.39, 64: 1.71 / 1.49
+// (with few taps the set-up warps cannot keep up).  PAR_B200_SINC_WS=0/1 or the PAR_SINC_KERNEL_* flags force one.
 static bool sinc_use_ws(int nt, int kernel) {
 	if (kernel) return kernel == 2;
 	static const int forced = [] { const char *e = getenv("PAR_B200_SINC_WS"); return e && (e[0] == '0' || e[0] == '1') ? e[0] - '0' : -1; }();
