@@ -168,10 +168,22 @@ def ncu_traffic(kernel):
 def workload_config(workload, world=1, channels_per_gpu=None, m=None):
     """The `config` object of a line -- identical for the GPU arm and the reference arm of one workload."""
     sr, dur, ch, desc = WORKLOADS[workload]
+    C = ch if channels_per_gpu is None else channels_per_gpu
+    n = int(sr * dur)
     cfg = {"workload": f"{workload}: {desc}", "sample_rate": sr, "seconds": dur,
-           "channels_per_gpu": ch if channels_per_gpu is None else channels_per_gpu, "samples_per_channel": int(sr * dur),
+           "channels_per_gpu": C, "samples_per_channel": n,
            "n_fft": N_FFT, "hop": HOP, "zeropad": 1, "window": "blackmanharris", "sinc_quality": NT,
            "speed_curve": "1 + 0.01 sin(2 pi 0.5556 t), one point per hop"}
+    if m is None:                       # the reference arm: length of the reference's speed_to_pos on this curve (CPU)
+        import oracle
+        curve = wow_curve(dur, sr)
+        m = len(oracle.speed_to_pos_c(np.ascontiguousarray(curve[:, 0] * sr), np.ascontiguousarray(curve[:, 1]), n))
+    T, F = n // HOP + 1, N_FFT // 2 + 1
+    cfg.update({"output_samples_per_channel": int(m),
+                "l2": "inputs (%.0f MB) and outputs (%.0f MB) per step exceed the 126 MB L2; no flush" % (
+                    C * n * 4 / 1e6, (C * T * F * 8 + C * m * 4 + m * 8) / 1e6),
+                "parallelism": (f"channels x{world}: every rank its own {C} channels; curve broadcast once before, output "
+                                f"lengths gathered once after the steps") if world > 1 else "1 GPU"})
     return cfg
 
 
@@ -290,7 +302,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 STFT / f64 sinc",
-            "data": "synthetic", "config": workload_config(args.workload),
+            "data": "synthetic", "config": workload_config(args.workload, max(1, args.gpus)),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -718,11 +730,6 @@ def main():
 
     if rank == 0:
         cfg = workload_config(args.workload, world, C, m)
-        cfg.update({"output_samples_per_channel": m,
-                    "l2": "inputs (%.0f MB) and outputs (%.0f MB) per step exceed the 126 MB L2; no flush" % (
-                        C * n * 4 / 1e6, (C * T * F * 8 + C * m * 4 + m * 8) / 1e6),
-                    "parallelism": (f"channels x{world}: every rank its own {C} channels; curve broadcast once before, output "
-                                    f"lengths gathered once after the steps") if world > 1 else "1 GPU"})
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling,
