@@ -793,7 +793,12 @@ static int positions_device(const double *sampletimes, const double *speeds, int
 	// job compute a slice each and all-gather them): nothing but the window's segments is uploaded then.
 	int rc;
 	const int64_t n_seg = k - 1;
-	const bool one_pass = !window && cap >= total && !ext_sums_dev;
+	// Two ways to the same bits.  Default: per-segment totals first (compute only, no position traffic), the host chain,
+	// then ONE expansion that writes every position once, offset included: DRAM traffic = the positions themselves.
+	// $PAR_B200_POS_ONE_PASS=1: expand the bare cumsums first and add the offsets in a second streaming pass (round 1:
+	// the same time, 2.8x the traffic).
+	static const bool want_one_pass = [] { const char *e = getenv("PAR_B200_POS_ONE_PASS"); return e && e[0] == '1'; }();
+	const bool one_pass = want_one_pass && !window && cap >= total && !ext_sums_dev;
 	// pinned layout: [speeds k][seg_n n_seg][seg_start n_seg][sums n_seg][off n_seg]
 	const size_t bytes = ((size_t)k + 4 * (size_t)n_seg) * 8;
 	char *pin = g_pinned.get(bytes);
