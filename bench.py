@@ -747,7 +747,8 @@ def main():
                                   {"note": "stft_tma_kernel<11,0>: TMA-staged frames, HBM-bound by design"}),
             "roofline_positions": roof(bytes_pos, k_pos, "expand_positions_kernel",
                                        {"note": "stage time includes the serial host chain of speed_to_pos (2 stream "
-                                                "synchronisations); kernels: expand_positions + add_offsets"}),
+                                                "synchronisations); kernels: segment_sums (totals) + expand_positions "
+                                                "(every position written once, offset included)"}),
             "stage_ms": {"stft": k_stft, "positions": k_pos, "sinc": k_sinc,
                          "note": "measured in 3 serial steps before the timed region; in the timed steps speed_to_pos runs on a "
                                  "side stream beside the STFT"},
